@@ -1,0 +1,458 @@
+"""sm_100a emitter for BK1: species net production rates + heat release rate.
+
+Emits one mechanism-specialised CUDA kernel (text) from the Mechanism IR.  What the kernel computes is
+what the reference's `productionRates` OKL kernel computes around its generated `kinetix_species_rates`
+and `kinetix_enthalpy_RT` (reference benchmark/okl/productionRates.okl:10-64,
+kinetix/core/reaction_rates.py:291-416,549-613, thermodynamics.py:65-80); HOW it is computed is
+re-designed for the B200 FP64 pipe:
+
+  * one thread = one state; all loads/stores species-major and coalesced (row k at k*offset + id);
+  * every constant lives in one `__constant__` pool `kc[]` addressed with literal indices, so FP64
+    instructions take constant-bank / uniform-register operands instead of materialising 64-bit
+    immediates with pairs of MOVs (the reference-style kernel spends >25 % of its issue slots on that);
+  * "minimal form": one exp(g_k) and one reciprocal per species (not one exp per reversible
+    reaction), equilibrium constants as products of those; rate constants that share (beta, Ta) share
+    one exp; distinct third-body efficiency vectors are evaluated once; log10(Pr) of falloff reactions
+    is obtained from the exponent of Pr and ln(M) per distinct collider instead of a log per reaction;
+    Troe terms that are exactly 0 or 1 over the validity range are folded at generation time;
+  * exp/log/reciprocal are the short sequences of csrc/kx_math.cuh.
+
+Results agree with the reference's generated code to rounding-level differences (per-state scaled
+error ~1e-14; the parity bound is 1e-10, tests/test_parity_gpu.py).
+"""
+import math
+
+from . import constants as const
+
+T_VALID_LO = 200.0      # the emitter proves exp() arguments stay in range for T in this interval
+T_VALID_HI = 6000.0
+EXP_SAFE = 690.0
+
+
+class ConstPool:
+    """De-duplicated pool of double constants -> `kc[i]` references."""
+
+    def __init__(self, name='kc'):
+        self.name = name
+        self.values = []
+        self._index = {}
+
+    def __call__(self, v):
+        v = float(v)
+        key = v.hex()
+        if key not in self._index:
+            self._index[key] = len(self.values)
+            self.values.append(v)
+        return f'{self.name}[{self._index[key]}]'
+
+    def definition(self, ctype='double'):
+        vals = self.values or [0.0]
+        body = ',\n  '.join(', '.join(_lit(v) for v in vals[i:i + 4]) for i in range(0, len(vals), 4))
+        return f'__constant__ {ctype} {self.name}[{len(vals)}] = {{\n  {body}\n}};\n'
+
+
+def _lit(v):
+    if math.isinf(v):
+        return 'CUDART_INF' if v > 0 else '-CUDART_INF'
+    return repr(float(v))
+
+
+def _arg_range(c0, c_lnT, c_rcpT, c_T=0.0):
+    """Conservative range of c0 + c_lnT*ln T + c_rcpT/T + c_T*T over the validity interval."""
+    lo = hi = c0
+    for c, a, b in ((c_lnT, math.log(T_VALID_LO), math.log(T_VALID_HI)),
+                    (c_rcpT, 1 / T_VALID_HI, 1 / T_VALID_LO),
+                    (c_T, T_VALID_LO, T_VALID_HI)):
+        x, y = c * a, c * b
+        lo += min(x, y)
+        hi += max(x, y)
+    return lo, hi
+
+
+def _exp_fn(lo, hi):
+    return 'kx_exp' if (lo > -EXP_SAFE and hi < EXP_SAFE) else 'kx_exp_wide'
+
+
+class BK1Emitter:
+    def __init__(self, mech, K=None):
+        self.m = mech
+        self.N = mech.n_species
+        self.K = K or ConstPool()
+        self.lines = []
+        self.stats = dict(exp=0, exp_wide=0, log=0, rcp=0)
+
+    # ------------------------------------------------------------------------------------------
+    def w(self, s=''):
+        self.lines.append('  ' + s if s else '')
+
+    def exp(self, arg_expr, lo, hi):
+        fn = _exp_fn(lo, hi)
+        self.stats['exp' if fn == 'kx_exp' else 'exp_wide'] += 1
+        return f'{fn}({arg_expr})'
+
+    # ---- thermo ------------------------------------------------------------------------------
+    def nasa_select(self, k, make):
+        """coefficient list for species k selected on T <= T_mid; `make(a)` maps the 7 NASA
+        coefficients to the derived coefficients actually needed."""
+        s = self.m.species[k]
+        lo, hi = make(s.nasa_lo), make(s.nasa_hi)
+        flag = self.tmid_flag(s.T_mid)
+        out = []
+        for a, b in zip(lo, hi):
+            out.append(self.K(a) if a == b else f'({flag} ? {self.K(a)} : {self.K(b)})')
+        return out, lo, hi
+
+    def tmid_flag(self, tmid):
+        name = 'lo_' + repr(float(tmid)).replace('.', '_').replace('-', 'm')
+        if name not in self._flags:
+            self._flags[name] = f'const bool {name} = T <= {_lit(float(tmid))};'
+        return name
+
+    # ---- Arrhenius ---------------------------------------------------------------------------
+    def arrhenius_group_expr(self, A, b, Ta):
+        """Expression for A T^b exp(-Ta/T) with the reference's literal special cases
+        (reaction_rates.py:218-241)."""
+        K = self.K
+        if b == 0 and Ta == 0:
+            return K(A)
+        if Ta == 0 and b in (-2, -1, 1, 2):
+            return {-2: f'{K(A)} * rcpT * rcpT', -1: f'{K(A)} * rcpT', 1: f'{K(A)} * T', 2: f'{K(A)} * T * T'}[b]
+        lnA = math.log(A)
+        if b == 0:
+            lo, hi = _arg_range(lnA, 0, -Ta)
+            return self.exp(f'fma({K(-Ta)}, rcpT, {K(lnA)})', lo, hi)
+        if Ta == 0:
+            lo, hi = _arg_range(lnA, b, 0)
+            return self.exp(f'fma({K(b)}, lnT, {K(lnA)})', lo, hi)
+        lo, hi = _arg_range(lnA, b, -Ta)
+        return self.exp(f'fma({K(b)}, lnT, fma({K(-Ta)}, rcpT, {K(lnA)}))', lo, hi)
+
+    def ratio_expr(self, rx):
+        """k0/k_inf as the reference forms it (one exponential of differences, or the constant
+        A0/A_inf -- reaction_rates.py:244-259).  Returns (expression, ln-argument expression or None)."""
+        K = self.K
+        A_inf, b_inf, E_inf = rx.rate.A, rx.rate.b, rx.rate.Ta
+        A0, b0, E0 = rx.k0.A, rx.k0.b, rx.k0.Ta
+        if (A0 - A_inf) != 0 and ((b0 - b_inf) != 0 or (E0 - E_inf) != 0):
+            c0 = math.log(A0) - math.log(A_inf)
+            cl = (b0 - b_inf)
+            cr = (-E0 + E_inf)
+            arg = K(c0)
+            if cl != 0:
+                arg = f'fma({K(cl)}, lnT, {arg})'
+            if cr != 0:
+                arg = f'fma({K(cr)}, rcpT, {arg})'
+            lo, hi = _arg_range(c0, cl, cr)
+            return arg, (lo, hi)
+        return None, A0 / A_inf
+
+    # ---- main --------------------------------------------------------------------------------
+    def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2):
+        m, N, K = self.m, self.N, self.K
+        self._flags = {}
+        body = []
+        self.lines = body
+        w = self.w
+        NA = m.n_active
+
+        # ---- state decode (productionRates.okl:11-41) ----
+        w('const double T = Tref * kx_ld_stream(state + id);')
+        w('const double rcpT = kx_rcp(T);')
+        w('const double lnT = kx_log(T);')
+        w(f'double C[{N}];')
+        w('{')
+        w('  double rcpMbar = 0.0;')
+        for k in range(N):
+            w(f'  C[{k}] = fmax(0.0, kx_ld_stream(sp + {k} * offset)) * {K(1. / m.species[k].M)}; rcpMbar += C[{k}];')
+        w('  const double rho = pressure_R * rcpT * kx_rcp(rcpMbar);')
+        for k in range(N):
+            w(f'  C[{k}] *= rho;')
+        w('}')
+        flag_pos = len(body)
+
+        # ---- which exp(+-g_k) are needed ----
+        need_pos = [False] * N   # exp(+g): species is a net product of a reversible reaction
+        need_neg = [False] * N   # exp(-g): net reactant
+        for rx in m.reactions:
+            if rx.reversible:
+                for k, v in enumerate(rx.nu_net):
+                    if v > 0:
+                        need_pos[k] = True
+                    elif v < 0:
+                        need_neg[k] = True
+
+        # g_k/RT = b0 + b1 lnT + b6/T + T (b2 + T (b3 + T (b4 + T b5)))       (reaction_rates.py:565-569)
+        def gcoef(a):
+            return [a[0] - a[6], -a[0], -a[1] / 2, (1. / 3. - 1. / 2.) * a[2], (1. / 4. - 1. / 3.) * a[3],
+                    (1. / 5. - 1. / 4.) * a[4], a[5]]
+
+        w(f'double EG[{N}], RG[{N}];   // exp(+g_k/RT), exp(-g_k/RT)')
+        for k in range(N):
+            if not (need_pos[k] or need_neg[k]):
+                continue
+            c, lo, hi = self.nasa_select(k, gcoef)
+            # range of g over the validity interval (sampled; polynomial is smooth)
+            gmin, gmax = float('inf'), float('-inf')
+            s = m.species[k]
+            for i in range(200):
+                t = T_VALID_LO + (T_VALID_HI - T_VALID_LO) * i / 199
+                b = gcoef(s.nasa_lo if t <= s.T_mid else s.nasa_hi)
+                g = b[0] + b[1] * math.log(t) + b[6] / t + t * (b[2] + t * (b[3] + t * (b[4] + t * b[5])))
+                gmin, gmax = min(gmin, g), max(gmax, g)
+            w('{')
+            w(f'  const double g = fma(fma(fma(fma({c[5]}, T, {c[4]}), T, {c[3]}), T, {c[2]}), T, '
+              f'fma({c[1]}, lnT, fma({c[6]}, rcpT, {c[0]})));')
+            if need_pos[k]:
+                w(f'  EG[{k}] = {self.exp("g", gmin * 1.05 - 5, gmax * 1.05 + 5)};')
+                if need_neg[k]:
+                    w(f'  RG[{k}] = kx_rcp(EG[{k}]);')
+                    self.stats['rcp'] += 1
+            else:
+                w(f'  RG[{k}] = {self.exp("-g", -gmax * 1.05 - 5, -gmin * 1.05 + 5)};')
+            w('}')
+
+        # ---- third bodies ----
+        w('double Cm = 0.0;')
+        for k in range(N):
+            w(f'Cm += C[{k}];')
+        w(f'const double C0 = {K(const.ONE_ATM / const.R_GAS)} * rcpT;')
+        w(f'const double rcpC0 = {K(const.R_GAS / const.ONE_ATM)} * T;')
+        # distinct efficiency vectors are evaluated once (declared here, at function scope)
+        eff_names = {}
+        for rx in m.reactions:
+            if rx.efficiencies is not None and tuple(rx.efficiencies) not in eff_names:
+                name = f'M{len(eff_names)}'
+                eff_names[tuple(rx.efficiencies)] = name
+                expr = 'Cm'
+                for k, e in enumerate(rx.efficiencies):
+                    if e != 1:
+                        expr = f'fma({K(e - 1)}, C[{k}], {expr})'
+                w(f'const double {name} = {expr};')
+
+        def collider(rx):
+            if rx.efficiencies is not None:
+                return eff_names[tuple(rx.efficiencies)]
+            if rx.third_body_index >= 0:
+                return f'C[{rx.third_body_index}]'
+            return 'Cm'
+
+        # ln(M) once per distinct collider of a Troe reaction whose Pr is formed as exp(.)*M
+        # (guarded like the reference's log10(Pr + CFLOAT_MIN))
+        ln_collider = {}
+        for rx in m.reactions:
+            if rx.kind == 'Troe':
+                name = collider(rx)
+                arg, _ = self.ratio_expr(rx)
+                if arg is not None and not name.startswith('C[') and name not in ln_collider:
+                    v = 'ln_' + name
+                    w(f'const double {v} = kx_log(fmax({name}, 1e-300));')
+                    self.stats['log'] += 1
+                    ln_collider[name] = v
+
+        def ln_of(name):
+            return ln_collider[name]
+
+        w(f'double wd[{N}];')
+        for k in range(N):
+            w(f'wd[{k}] = 0.0;')
+
+        # ---- reactions, grouped by shared (beta, Ta) of the main rate constant ----
+        groups = {}
+        for i, rx in enumerate(m.reactions):
+            if rx.kind == 'P-log':
+                key = ('plog', i)
+            else:
+                b, Ta = rx.rate.b, rx.rate.Ta
+                trivial = (b == 0 and Ta == 0) or (Ta == 0 and b in (-2, -1, 1, 2))
+                key = (b, Ta, i) if trivial else (b, Ta)
+            groups.setdefault(key, []).append(i)
+
+        def conc_product(nu):
+            terms = []
+            for k, c in enumerate(nu):
+                terms += [f'C[{k}]'] * c
+            return ' * '.join(terms)
+
+        for gi, (key, members) in enumerate(groups.items()):
+            first = m.reactions[members[0]]
+            w(f'// ---- rate-constant group {gi}: ' + '; '.join(str(i + 1) for i in members))
+            w('{')
+            if first.kind != 'P-log':
+                w(f'  const double kbase = {self.arrhenius_group_expr(first.rate.A, first.rate.b, first.rate.Ta)};')
+            for i in members:
+                rx = m.reactions[i]
+                w(f'  // {i + 1}: {rx.equation}')
+                w('  {')
+                if rx.kind == 'P-log':
+                    self._emit_plog(rx)
+                elif i == members[0]:
+                    w('    double kf = kbase;')
+                else:
+                    w(f'    double kf = kbase * {K(rx.rate.A / first.rate.A)};')
+
+                if rx.kind == 'three-body':
+                    w(f'    kf *= {collider(rx)};')
+                elif rx.kind in ('pressure-modification', 'Troe', 'SRI'):
+                    M = collider(rx)
+                    arg, rng = self.ratio_expr(rx)
+                    if arg is not None:
+                        w(f'    const double lnr = {arg};')
+                        w(f'    const double Pr = {self.exp("lnr", *rng)} * {M};')
+                    else:
+                        w(f'    const double Pr = {K(rng)} * {M};')
+                    w('    const double rcp1Pr = kx_rcp(1.0 + Pr);')
+                    self.stats['rcp'] += 1
+                    if rx.kind == 'pressure-modification':
+                        w('    kf *= Pr * rcp1Pr;')
+                    elif rx.kind == 'Troe':
+                        # log10(Pr + CFLOAT_MIN): from the exponent and ln(M) when M is a sum of
+                        # concentrations; literally when the collider is a single species (can be 0)
+                        if arg is not None and not M.startswith('C['):
+                            w(f'    const double logPr = (lnr + {ln_of(M)}) * {K(1 / math.log(10))};')
+                        else:
+                            w('    const double logPr = kx_log10(Pr + 1e-300);')
+                            self.stats['log'] += 1
+                        w(f'    const double Fc = {self._troe_fcent(rx.troe)};')
+                        w('    const double lnFc = kx_log(Fc);')
+                        self.stats['log'] += 1
+                        w(f'    const double logFc = lnFc * {K(1 / math.log(10))};')
+                        w('    const double tc = fma(-0.67, logFc, -0.4) + logPr;')
+                        w('    const double tn = fma(-1.27, logFc, 0.75) - 0.14 * tc;')
+                        # F = 10^(logFc/(1+(tc/tn)^2)) = exp(lnFc * tn^2/(tn^2+tc^2))
+                        w('    const double tn2 = tn * tn;')
+                        w('    const double F = kx_exp(lnFc * tn2 * kx_rcp(fma(tc, tc, tn2)));')
+                        self.stats['exp'] += 1
+                        self.stats['rcp'] += 1
+                        w('    kf *= Pr * rcp1Pr * F;')
+                    else:  # SRI (reaction_rates.py:346-357)
+                        s = rx.sri
+                        w('    const double logPr = kx_log10(Pr);')
+                        w(f'    const double sb = {K(s["A"])} * kx_exp_wide({K(-s["B"])} * rcpT) + '
+                          f'kx_exp_wide({K(-1. / (s["C"] + const.FLOAT_MIN))} * T);')
+                        w(f'    double F = {K(s["D"])} * kx_pow(sb, kx_rcp(fma(logPr, logPr, 1.0)));')
+                        if s['E'] != 0:
+                            w(f'    F *= kx_exp({K(s["E"])} * lnT);')
+                        self.stats['log'] += 2
+                        self.stats['exp'] += 3
+                        w('    kf *= Pr * rcp1Pr * F;')
+
+                Rf = conc_product(rx.nu_reac)
+                net = rx.nu_net
+                if not rx.reversible:
+                    w(f'    const double q = kf * {Rf};')
+                else:
+                    # 1/Kc = prod exp(g)^nu * C0^(-sum nu); interleave +g / -g factors so partial
+                    # products stay O(exp(delta g)) (no intermediate over/underflow)
+                    pos = [f'EG[{k}]' for k, v in enumerate(net) if v > 0 for _ in range(v)]
+                    neg = [f'RG[{k}]' for k, v in enumerate(net) if v < 0 for _ in range(-v)]
+                    factors = []
+                    while pos or neg:
+                        if pos:
+                            factors.append(pos.pop(0))
+                        if neg:
+                            factors.append(neg.pop(0))
+                    sn = sum(net)
+                    factors += ['C0' if sn < 0 else 'rcpC0'] * abs(sn)
+                    w(f'    const double kr = {" * ".join(factors)};')
+                    Rr = conc_product(rx.nu_prod)
+                    w(f'    const double q = kf * fma(-kr, {Rr}, {Rf});')
+                for k, v in enumerate(net):
+                    if v == 1:
+                        w(f'    wd[{k}] += q;')
+                    elif v == -1:
+                        w(f'    wd[{k}] -= q;')
+                    elif v != 0:
+                        w(f'    wd[{k}] = fma({float(v)}, q, wd[{k}]);')
+                w('  }')
+            w('}')
+
+        # ---- outputs (productionRates.okl:48-62) ----
+        def hcoef(a):
+            return [a[0], a[1] / 2, a[2] / 3, a[3] / 4, a[4] / 5, a[5]]
+
+        w('double hsum = 0.0;')
+        for k in range(N):
+            c, _, _ = self.nasa_select(k, hcoef)
+            w(f'kx_st_stream(out + {k} * offset, {K(m.species[k].M)} * wd[{k}]);')
+            w(f'hsum = fma(wd[{k}], fma(fma(fma(fma({c[4]}, T, {c[3]}), T, {c[2]}), T, {c[1]}), T, '
+              f'fma({c[5]}, rcpT, {c[0]})), hsum);')
+        w(f'kx_st_stream(rates + id, {K(-const.R_GAS)} * T * hsum);')
+
+        body[flag_pos:flag_pos] = ['  ' + v for v in self._flags.values()]
+
+        head = [
+            f'// BK1 (species production rates): {m.name}, {N} species / {m.n_reactions} reactions; '
+            f'{self.stats["exp"]} kx_exp, {self.stats["exp_wide"]} wide exp, {self.stats["log"]} log, '
+            f'{self.stats["rcp"]} rcp per state',
+            f'extern "C" __global__ void __launch_bounds__({block}, {min_blocks})',
+            f'{kernel_name}(const long long n_states, const long long offsetT, const long long offset,',
+            '           const double pressure_R, const double P, const double lnP,',
+            '           const double* __restrict__ state, double* __restrict__ rates, const double Tref)',
+            '{',
+            '  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;',
+            '  if (id >= n_states) return;',
+            '  const double* sp = state + id + offsetT;',
+            '  double* out = rates + id + offsetT;',
+        ]
+        return '\n'.join(head + body + ['}', ''])
+
+    # ------------------------------------------------------------------------------------------
+    def _troe_fcent(self, tr):
+        """(1-A) exp(-T/T3) + A exp(-T/T1) [+ exp(-T2/T)] with the reference's A in {0,1} special
+        cases (reaction_rates.py:331-340); terms that are exactly 0 or 1 in double over the whole
+        validity range of T are folded."""
+        K = self.K
+        terms = []
+
+        def texp(coef_T, weight):
+            # weight * exp(coef_T * T)
+            lo, hi = sorted((coef_T * T_VALID_LO, coef_T * T_VALID_HI))
+            if hi < -750.0:
+                return None                       # exactly 0
+            if abs(lo) < 1e-17 and abs(hi) < 1e-17:
+                return K(weight)                  # exp() == 1 exactly
+            e = self.exp(f'{K(coef_T)} * T', lo, hi)
+            return e if weight == 1 else f'{K(weight)} * {e}'
+
+        A = tr['A']
+        if A == 0:
+            parts = [texp(-1. / (tr['T3'] + const.FLOAT_MIN), 1.0)]
+        elif A == 1:
+            parts = [texp(-1. / (tr['T1'] + const.FLOAT_MIN), 1.0)]
+        else:
+            parts = [texp(-1. / (tr['T3'] + const.FLOAT_MIN), 1 - A), texp(-1. / (tr['T1'] + const.FLOAT_MIN), A)]
+        if tr['T2'] < float('inf'):
+            lo, hi = sorted((-tr['T2'] / T_VALID_LO, -tr['T2'] / T_VALID_HI))
+            parts.append(self.exp(f'{K(-tr["T2"])} * rcpT', lo, hi))
+        parts = [p for p in parts if p is not None]
+        return ' + '.join(parts) if parts else '0.0'
+
+    def _emit_plog(self, rx):
+        """Pressure-dependent Arrhenius: ln k linear in ln P between tabulated pressures; the pressure
+        is uniform over a launch so the branch chain is warp-uniform (reaction_rates.py:358-388)."""
+        K, w = self.K, self.w
+
+        def ksum(ks):
+            return ' + '.join(self.arrhenius_group_expr(k.A, k.b, k.Ta) for k in ks)
+
+        pl = rx.plog
+        n = len(pl)
+        w('    double kf;')
+        for i in range(n - 1):
+            (p1, k1), (p2, k2) = pl[i], pl[i + 1]
+            lnp1, lnp2 = math.log(p1), math.log(p2)
+            w(f'    {"if" if i == 0 else "} else if"} ((P > {_lit(p1)}) && (P < {_lit(p2)})) {{')
+            w(f'      const double l1 = kx_log({ksum(k1)}), l2 = kx_log({ksum(k2)});')
+            w(f'      kf = kx_exp(fma((l2 - l1) * (lnP - {K(lnp1)}), {K(1 / (lnp2 - lnp1))}, l1));')
+            self.stats['log'] += 2
+            self.stats['exp'] += 1
+            if i == 0:
+                w(f'    }} else if (P <= {_lit(p1)}) {{')
+                w(f'      kf = {ksum(k1)};')
+            else:
+                w(f'    }} else if (P == {_lit(p1)}) {{')
+                w(f'      kf = {ksum(k1)};')
+            if i == n - 2:
+                w(f'    }} else if (P >= {_lit(p2)}) {{')
+                w(f'      kf = {ksum(k2)};')
+        w('    } else { kf = 0.0; }')

@@ -1,0 +1,114 @@
+// kx_math.cuh -- FP64 / FP32 math primitives for the generated BK1/BK2 kernels (sm_100a).
+//
+// Both hot paths are FP64-pipe bound on B200 (64 DFMA lanes/clk/SM): what matters is the number of
+// FP64-pipe instructions per transcendental, not bytes.  libdevice's exp/log/div cost 18 / 30 / ~10
+// FP64 instructions plus special-case handling the kernels do not need (arguments are finite and in a
+// known range).  The versions here are branch-light, accurate to <= 2 ulp (measured against mpmath,
+// tools/fit_math_polys.py) and cost
+//
+//     kx_exp   15 FP64  (Cody-Waite reduction + degree-11 polynomial, exponent patched with integer ops)
+//     kx_log   ~17 FP64 (atanh series in s=(m-1)/(m+1), reciprocal by MUFU.RCP64H + Newton)
+//     kx_rcp    5 FP64 + 1 MUFU
+//
+// The reference relies on the backend's libm for these (benchmark/src/kinetix.cpp:246-251 maps
+// __KINETIX_EXP__/LOG__/LOG10__/POW__ onto exp/log/log10/pow); parity is to 1e-10, not bit-wise.
+#pragma once
+#include <cuda_runtime.h>
+
+#define KX_DEVICE __device__ __forceinline__
+
+// ---- reciprocal ------------------------------------------------------------------------------
+// MUFU.RCP64H seed + (cubic, then quadratic) Newton steps: error e0^6, no range checks.
+// Valid for normal, finite, non-zero |a| in about [1e-300, 1e300] -- all uses satisfy this.
+KX_DEVICE double kx_rcp(double a)
+{
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  e = fma(e, e, e);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
+// a / b with the reciprocal above (one extra DMUL); relative error ~2e-16.
+KX_DEVICE double kx_div(double a, double b) { return a * kx_rcp(b); }
+
+// ---- exp -------------------------------------------------------------------------------------
+// exp(x), x finite.  The exponent is clamped to the normal range with two integer min/max (ALU pipe),
+// so results saturate at ~2^-1022 / ~2^1023 instead of going through denormals / inf: absolute
+// differences of < 1e-307 against libm.  The emitter proves |x| < 700 for every call it routes here
+// over the validity range of T (interval arithmetic at generation time) and uses kx_exp_wide otherwise.
+KX_DEVICE double kx_exp(double x)
+{
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
+  double kd = fma(x, 1.4426950408889634, MAGIC);
+  int k = __double2loint(kd);
+  kd -= MAGIC;
+  double r = fma(kd, -6.93147180369123816490e-01, x);   // ln2 high part (32 trailing zero bits)
+  r = fma(kd, -1.90821492927058770002e-10, r);          // ln2 low part
+  double p = 2.5110037605963777e-08;
+  p = fma(p, r, 2.763263963904103e-07);
+  p = fma(p, r, 2.755724091857897e-06);
+  p = fma(p, r, 2.4801485482328494e-05);
+  p = fma(p, r, 0.00019841269890047113);
+  p = fma(p, r, 0.0013888888952314775);
+  p = fma(p, r, 0.008333333333319601);
+  p = fma(p, r, 0.0416666666664881);
+  p = fma(p, r, 0.1666666666666668);
+  p = fma(p, r, 0.5000000000000019);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  k = max(min(k, 1022), -1021);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// Full-range exp (libdevice): underflow to 0 / overflow to inf exactly like the reference's libm.
+KX_DEVICE double kx_exp_wide(double x) { return exp(x); }
+
+// ---- log -------------------------------------------------------------------------------------
+// log(x) for normal positive finite x.  x = 2^e * m with m in [sqrt(1/2), sqrt(2)),
+// log(m) = 2 atanh(s), s = (m-1)/(m+1), atanh(s)/s = 1 + z q(z), z = s^2, |s| <= 0.1716.
+KX_DEVICE double kx_log(double x)
+{
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  // bring the mantissa into [sqrt(.5), sqrt(2)): subtract the high word of sqrt(.5) (0x3fe6a09e)
+  int e = (hi - 0x3fe6a09e) >> 20;
+  hi -= e << 20;
+  const double m = __hiloint2double(hi, lo);
+  const double s = (m - 1.0) * kx_rcp(m + 1.0);
+  const double z = s * s;
+  double q = 0.07308224842521703;
+  q = fma(q, z, 0.07665860800278021);
+  q = fma(q, z, 0.09091444562630861);
+  q = fma(q, z, 0.1111110556739754);
+  q = fma(q, z, 0.14285714312987743);
+  q = fma(q, z, 0.19999999999949752);
+  q = fma(q, z, 0.3333333333333335);
+  const double s2 = s + s;
+  const double lm = fma(s2 * z, q, s2);
+  const double ed = (double)e;
+  // e*ln2 split so that the high product is exact for |e| < 2^11
+  return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, lm));
+}
+
+KX_DEVICE double kx_log10(double x) { return kx_log(x) * 0.4342944819032518; }
+
+// x^y for x > 0 and 10^x
+KX_DEVICE double kx_pow(double x, double y) { return kx_exp(y * kx_log(x)); }
+KX_DEVICE double kx_exp10(double x) { return kx_exp(x * 2.302585092994046); }
+
+// ---- streaming global access -----------------------------------------------------------------
+// State rows are read once and result rows written once: keep them out of L1 and mark evict-first.
+KX_DEVICE double kx_ld_stream(const double* p)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+KX_DEVICE void kx_st_stream(double* p, double v)
+{
+  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}

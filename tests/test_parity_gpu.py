@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA path (through the C ABI / host mirror) against the oracle.
+
+Bound: FP64 per-state scaled error <= 1e-10 (BASELINE.json north_star; norm of SURVEY.md 8c), plus the
+reference's own Cantera known-answer files at the reference's tolerances (bk.cpp:198-199,258,148).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests.common import Oracle, R, bk1_errors, mech_path, rel_err
+from oracle.port import load_cantera_ci, synthetic_states
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+P_ATM = 101325.0
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'ci_data')
+
+
+@pytest.fixture(scope='module')
+def kinetix():
+    import kinetix_b200.host as kx
+    yield kx
+    kx.finalize()
+
+
+def _setup(kx, mech, p_ref=P_ATM, T_ref=1.0):
+    kx.init(mech_path(mech))
+    N = kx.nSpecies()
+    kx.build(p_ref, T_ref, [1.0 / N] * N, True)
+    return N
+
+
+def _run_bk1(kx, st, pressure_nd):
+    S = st.shape[1]
+    d_state = torch.from_numpy(st).cuda()
+    d_rates = torch.full_like(d_state, float('nan'))
+    kx.productionRates(S, S, S, pressure_nd, d_state, d_rates)
+    torch.cuda.synchronize()
+    return d_rates.cpu().numpy()
+
+
+def _run_bk2(kx, st, pressure_nd):
+    N, S = st.shape[0] - 1, st.shape[1]
+    d_state = torch.from_numpy(st).cuda()
+    visc = torch.full((S,), float('nan'), dtype=torch.float64, device='cuda')
+    cond = torch.full_like(visc, float('nan'))
+    rhoD = torch.full((N, S), float('nan'), dtype=torch.float64, device='cuda')
+    kx.mixtureAvgTransportProps(S, S, S, pressure_nd, d_state, visc, cond, rhoD)
+    torch.cuda.synchronize()
+    return cond.cpu().numpy(), visc.cpu().numpy(), rhoD.cpu().numpy()
+
+
+@pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
+def test_bk1_matches_oracle_on_random_states(kinetix, mech):
+    N = _setup(kinetix, mech)
+    assert kinetix.modulePath().endswith('libkx_mech.so')
+    orc = Oracle(mech)
+    st = synthetic_states(N, 20000, seed=1234)
+    new = _run_bk1(kinetix, st, 1.0)
+    ref = orc.production_rates(st, P_ATM)
+    assert np.isfinite(new).all()
+    rate_err, hrr_err = bk1_errors(new, ref)
+    print(f'{mech} BK1 vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}')
+    assert rate_err <= TOL and hrr_err <= TOL
+
+
+@pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
+def test_bk2_matches_oracle_on_random_states(kinetix, mech):
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech)
+    st = synthetic_states(N, 20000, seed=4321)
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    errs = rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)
+    print(f'{mech} BK2 vs {orc.kind}: cond {errs[0]:.3e} visc {errs[1]:.3e} rhoD {errs[2]:.3e}')
+    assert max(errs) <= TOL
+
+
+@pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
+def test_thermo_matches_oracle(kinetix, mech):
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech)
+    st = synthetic_states(N, 5000, seed=99)
+    S = st.shape[1]
+    d_state = torch.from_numpy(st).cuda()
+    rho = torch.empty(S, dtype=torch.float64, device='cuda')
+    cp = torch.empty((N, S), dtype=torch.float64, device='cuda')
+    rcp = torch.empty(S, dtype=torch.float64, device='cuda')
+    kinetix.thermodynamicProps(S, S, S, 1.0, d_state, rho, cp, rcp)
+    torch.cuda.synchronize()
+    a, b, c = orc.thermo(st, P_ATM)
+    errs = rel_err(rho.cpu().numpy(), a), rel_err(cp.cpu().numpy(), b), rel_err(rcp.cpu().numpy(), c)
+    print(f'{mech} thermo: {errs}')
+    assert max(errs) <= 1e-13
+
+
+@pytest.mark.parametrize('mech,states', [('gri30', ['initial', 'ignition', 'final']),
+                                          ('LiDryer', ['initial', 'ignition'])])
+def test_cantera_known_answers(kinetix, mech, states):
+    """The reference's --cimode 1 check (bk.cpp:503-520,629-642,182-200,258): state 0 is the reference
+    state, rates converted back to molar and compared with Cantera."""
+    kinetix.init(mech_path(mech))
+    N = kinetix.nSpecies()
+    cis = [load_cantera_ci(os.path.join(GOLDEN, f'{mech}.{s}.cantera'), N) for s in states]
+    M = np.array(kinetix.molarMasses())
+    assert np.max(np.abs(M - cis[0]['M']) / M) < 1e-7          # species-order guard (bk.cpp:291-305)
+    p_ref, T_ref = cis[0]['p'], cis[0]['T']
+    kinetix.build(p_ref, T_ref, list(cis[0]['Y']), True)
+    S = len(cis)
+    st = np.empty((N + 1, S))
+    for i, c in enumerate(cis):
+        st[0, i] = c['T'] / T_ref
+        st[1:, i] = c['Y']
+    rates = _run_bk1(kinetix, st, cis[0]['p'] / p_ref)
+    cond, visc, rhoD = _run_bk2(kinetix, st, cis[0]['p'] / p_ref)
+    mw = np.array(kinetix.molecularWeights()) * kinetix.refMeanMolecularWeight()
+    for i, c in enumerate(cis):
+        molar = rates[1:, i] / mw
+        e = [abs(rates[0, i] - c['hrr']) / abs(c['hrr'])]
+        for k in range(kinetix.nActiveSpecies()):
+            e.append(abs(molar[k] - c['wdot'][k]) / abs(c['wdot'][k]) if abs(c['wdot'][k]) > 1e-50 else abs(molar[k]))
+        rtol = 5e-5 if i >= 2 else 2e-8
+        print(f'{mech}.{states[i]} rates error_inf {max(e):.3e} < {rtol}')
+        assert max(e) < rtol
+        et = max(abs(cond[i] - c['conductivity']) / c['conductivity'], abs(visc[i] - c['viscosity']) / c['viscosity'],
+                 np.max(np.abs(rhoD[:, i] - c['rhoD']) / c['rhoD']))
+        print(f'{mech}.{states[i]} transport error_inf {et:.3e} < 1e-3')
+        assert et < 1e-3
+
+
+def test_offsets_ref_state_and_ragged_sizes(kinetix):
+    """offsetT/offset addressing with a padded pitch, T_ref != 1, p != p_ref, and state counts that are
+    not multiples of the block size (including 1 and 0)."""
+    mech = 'LiDryer'
+    kinetix.init(mech_path(mech))
+    N = kinetix.nSpecies()
+    p_ref, T_ref = 2.0e5, 1000.0
+    kinetix.build(p_ref, T_ref, [1.0 / N] * N, True)
+    orc = Oracle(mech)
+    for S in (1, 31, 129, 1000):
+        pitch = S + 13
+        st = synthetic_states(N, S, seed=S, Tref=T_ref)
+        slab = np.full((N + 2) * pitch + 7, np.nan)
+        slab[0:S] = st[0]
+        offsetT = 7 + pitch                      # species rows start after a gap
+        for k in range(N):
+            slab[offsetT + k * pitch: offsetT + k * pitch + S] = st[k + 1]
+        d_state = torch.from_numpy(slab).cuda()
+        d_rates = torch.full_like(d_state, float('nan'))
+        p = 3.0e5
+        kinetix.productionRates(S, offsetT, pitch, p / p_ref, d_state, d_rates)
+        torch.cuda.synchronize()
+        out = d_rates.cpu().numpy()
+        new = np.empty_like(st)
+        new[0] = out[0:S]
+        for k in range(N):
+            new[k + 1] = out[offsetT + k * pitch: offsetT + k * pitch + S]
+        ref = orc.production_rates(st, p, Tref=T_ref)
+        rate_err, hrr_err = bk1_errors(new, ref)
+        assert rate_err <= TOL and hrr_err <= TOL, (S, rate_err, hrr_err)
+        # nothing outside the addressed rows may be written
+        mask = np.ones_like(out, dtype=bool)
+        mask[0:S] = False
+        for k in range(N):
+            mask[offsetT + k * pitch: offsetT + k * pitch + S] = False
+        assert np.isnan(out[mask]).all()
+    # zero states: no launch, no error
+    kinetix.productionRates(0, 0, 0, 1.0, None, None)
+
+
+def test_negative_mass_fractions_are_clamped(kinetix):
+    """Y_k < 0 is clamped to 0 before use (productionRates.okl:27, transportProps.okl:25)."""
+    mech = 'LiDryer'
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech)
+    st = synthetic_states(N, 256, seed=5)
+    st[1 + (np.arange(256) % N), np.arange(256)] *= -1.0
+    new = _run_bk1(kinetix, st, 1.0)
+    ref = orc.production_rates(st, P_ATM)
+    rate_err, hrr_err = bk1_errors(new, ref)
+    assert rate_err <= TOL and hrr_err <= TOL
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    assert max(rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)) <= TOL
+
+
+def test_host_buffer_entry_point_matches_device_path(kinetix):
+    mech = 'gri30'
+    N = _setup(kinetix, mech)
+    S = 3000
+    st = synthetic_states(N, S, seed=77)
+    dev = _run_bk1(kinetix, st, 1.0)
+    h_state = torch.from_numpy(st).pin_memory()
+    h_rates = torch.empty_like(h_state).pin_memory()
+    kinetix.productionRatesHost(S, S, S, 1.0, h_state, h_rates)
+    assert np.array_equal(h_rates.numpy(), dev)
+    c, v, rd = _run_bk2(kinetix, st, 1.0)
+    hv = torch.empty(S, dtype=torch.float64).pin_memory()
+    hc = torch.empty(S, dtype=torch.float64).pin_memory()
+    hrd = torch.empty((N, S), dtype=torch.float64).pin_memory()
+    kinetix.mixtureAvgTransportPropsHost(S, S, S, 1.0, h_state, hv, hc, hrd)
+    assert np.array_equal(hv.numpy(), v) and np.array_equal(hc.numpy(), c) and np.array_equal(hrd.numpy(), rd)
+
+
+def test_errors_are_loud(kinetix):
+    kinetix.finalize()
+    with pytest.raises(kinetix.KinetixError):
+        kinetix.productionRates(1, 1, 1, 1.0, 0, 0)            # not initialised
+    with pytest.raises(kinetix.KinetixError):
+        kinetix.init('/nonexistent/mech.yaml')
+    with pytest.raises(kinetix.KinetixError):
+        kinetix.init(mech_path('gri30'), tool='Pele')

@@ -1,0 +1,48 @@
+#!/usr/bin/env python3
+"""Quick device-side timing of BK1/BK2/thermo for one mechanism (development aid; bench.py is the contract)."""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import kinetix_b200.host as kinetix  # noqa: E402
+from oracle.port import synthetic_states  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--mech', default='gri30')
+ap.add_argument('--n', type=int, default=1 << 22)
+ap.add_argument('--reps', type=int, default=5)
+ap.add_argument('--cache', default=None)
+a = ap.parse_args()
+kinetix.init(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', a.mech + '.yaml'), cache_dir=a.cache)
+N = kinetix.nSpecies()
+kinetix.build(101325.0, 1.0, [1.0 / N] * N, True)
+S = a.n
+base = torch.from_numpy(synthetic_states(N, 1 << 16, seed=1)).cuda()
+st = base.repeat(1, S // (1 << 16)).contiguous()
+rates = torch.empty_like(st)
+visc = torch.empty(S, dtype=torch.float64, device='cuda')
+cond = torch.empty_like(visc)
+rhoD = torch.empty((N, S), dtype=torch.float64, device='cuda')
+
+
+def timeit(fn):
+    fn(); fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / a.reps
+
+
+t1 = timeit(lambda: kinetix.productionRates(S, S, S, 1.0, st, rates))
+t2 = timeit(lambda: kinetix.mixtureAvgTransportProps(S, S, S, 1.0, st, visc, cond, rhoD))
+t3 = timeit(lambda: kinetix.thermodynamicProps(S, S, S, 1.0, st, visc, rhoD, cond))
+print(f'{a.mech} S={S}: BK1 {t1:.3f} ms = {S / t1 / 1e6:.1f} Mstates/s | BK2 {t2:.3f} ms = {S / t2 / 1e6:.1f} Mstates/s | '
+      f'thermo {t3:.3f} ms = {S / t3 / 1e6:.1f} Mstates/s ({(2 * N + 3) * 8 * S / t3 / 1e6:.0f} GB/s)')
