@@ -32,13 +32,16 @@ EXP_SAFE = 690.0
 class ConstPool:
     """De-duplicated pool of double constants -> `kc[i]` references."""
 
-    def __init__(self, name='kc'):
+    def __init__(self, name='kc', inline=False):
         self.name = name
+        self.inline = inline        # emit literals (compiler materialises them) instead of pool loads
         self.values = []
         self._index = {}
 
     def __call__(self, v):
         v = float(v)
+        if self.inline and not math.isinf(v):
+            return f'({_lit(v)})'
         key = v.hex()
         if key not in self._index:
             self._index[key] = len(self.values)
@@ -70,7 +73,7 @@ def _arg_range(c0, c_lnT, c_rcpT, c_T=0.0):
 
 
 def _exp_fn(lo, hi):
-    return 'kx_exp' if (lo > -EXP_SAFE and hi < EXP_SAFE) else 'kx_exp_wide'
+    return 'kx_exp_nc' if (lo > -EXP_SAFE and hi < EXP_SAFE) else 'kx_exp_wide'
 
 
 class BK1Emitter:
@@ -87,8 +90,14 @@ class BK1Emitter:
 
     def exp(self, arg_expr, lo, hi):
         fn = _exp_fn(lo, hi)
-        self.stats['exp' if fn == 'kx_exp' else 'exp_wide'] += 1
+        self.stats['exp' if fn == 'kx_exp_nc' else 'exp_wide'] += 1
         return f'{fn}({arg_expr})'
+
+    def EG(self, k):
+        return f'gs[{self.eg_slot[k]} * {self.block}]' if self.gibbs_in_smem else f'eg{k}'
+
+    def RG(self, k):
+        return f'gs[{self.rg_slot[k]} * {self.block}]' if self.gibbs_in_smem else f'rg{k}'
 
     # ---- thermo ------------------------------------------------------------------------------
     def nasa_select(self, k, make):
@@ -146,31 +155,97 @@ class BK1Emitter:
             return arg, (lo, hi)
         return None, A0 / A_inf
 
+    # ---- reaction scheduling -----------------------------------------------------------------
+    def _units(self):
+        """Scheduling units: reactions sharing (beta, Ta) of their main rate constant form one unit (they
+        share one exp); everything else is a unit of one."""
+        groups = {}
+        for i, rx in enumerate(self.m.reactions):
+            if rx.kind == 'P-log':
+                key = ('plog', i)
+            else:
+                b, Ta = rx.rate.b, rx.rate.Ta
+                trivial = (b == 0 and Ta == 0) or (Ta == 0 and b in (-2, -1, 1, 2))
+                key = (b, Ta, i) if trivial else (b, Ta)
+            groups.setdefault(key, []).append(i)
+        return list(groups.values())
+
+    def _species_of_unit(self, unit):
+        s = set()
+        for i in unit:
+            rx = self.m.reactions[i]
+            for k in range(self.N):
+                if rx.nu_reac[k] or rx.nu_prod[k]:
+                    s.add(k)
+            if rx.efficiencies is None and rx.third_body_index >= 0 and rx.kind != 'elementary' \
+                    and rx.kind != 'irreversible':
+                s.add(rx.third_body_index)
+        return s
+
+    def _schedule(self, units, usp, reorder):
+        """Order the units so that few species are 'live' (first use .. last use) at any time: greedy
+        choice of the unit that opens the fewest new live ranges, closes the most and touches species
+        close to retirement.  For GRI-3.0 the peak live set drops from 41 to 25 species (mean 18), which is
+        what lets concentrations and rate accumulators of the live species stay in registers."""
+        if not reorder:
+            return list(range(len(units)))
+        count = [0] * self.N
+        for sp in usp:
+            for k in sp:
+                count[k] += 1
+        rem = list(count)
+        live, left, order = set(), set(range(len(units))), []
+        while left:
+            best = None
+            for ui in left:
+                new = len(usp[ui] - live)
+                ret = sum(1 for k in usp[ui] if rem[k] == 1)
+                close = sum(1.0 / rem[k] for k in usp[ui])
+                cost = new - 1.0 * ret - 2.0 * close
+                if best is None or cost < best[0] or (cost == best[0] and ui < best[1]):
+                    best = (cost, ui)
+            ui = best[1]
+            order.append(ui)
+            left.discard(ui)
+            live |= usp[ui]
+            for k in usp[ui]:
+                rem[k] -= 1
+                if rem[k] == 0:
+                    live.discard(k)
+        return order
+
     # ---- main --------------------------------------------------------------------------------
-    def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2):
+    def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
+             reorder=True, prefetch=4, ring=0, pin_loads=False):
+        """block / min_blocks: launch bounds.
+        sync_every: a CTA-wide barrier every that many reactions keeps the warps of a CTA inside the same
+          window of the straight-line code so instruction-cache fills are shared (0 = none).
+        gibbs_in_smem: exp(+-g_k) of live species in shared memory slots [slot][thread] (slots are recycled
+          when a species retires) instead of registers.
+        reorder: liveness-minimising reaction order (see _schedule).
+        prefetch: (ring == 0) the state row of a species is re-loaded this many ACTIVATIONS before its own.
+        ring: > 0: state rows are re-fetched with cp.async (LDGSTS) into a ring of that many shared-memory
+          slots per thread, one commit group per species in activation order; an activation waits with
+          cp.async.wait_group for ITS group only (FIFO), whereas a register load would wait on a counting
+          scoreboard shared with younger prefetches."""
         m, N, K = self.m, self.N, self.K
+        self.block, self.sync_every, self.gibbs_in_smem = block, sync_every, gibbs_in_smem
         self._flags = {}
         body = []
         self.lines = body
         w = self.w
-        NA = m.n_active
 
-        # ---- state decode (productionRates.okl:11-41) ----
-        w('const double T = Tref * kx_ld_stream(state + id);')
-        w('const double rcpT = kx_rcp(T);')
-        w('const double lnT = kx_log(T);')
-        w(f'double C[{N}];')
-        w('{')
-        w('  double rcpMbar = 0.0;')
-        for k in range(N):
-            w(f'  C[{k}] = fmax(0.0, kx_ld_stream(sp + {k} * offset)) * {K(1. / m.species[k].M)}; rcpMbar += C[{k}];')
-        w('  const double rho = pressure_R * rcpT * kx_rcp(rcpMbar);')
-        for k in range(N):
-            w(f'  C[{k}] *= rho;')
-        w('}')
-        flag_pos = len(body)
+        units = self._units()
+        usp = [self._species_of_unit(u) for u in units]
+        order = self._schedule(units, usp, reorder)
+        first, last = {}, {}
+        for pos, ui in enumerate(order):
+            for k in usp[ui]:
+                first.setdefault(k, pos)
+                last[k] = pos
+        self.schedule_stats = dict(units=len(units))
 
-        # ---- which exp(+-g_k) are needed ----
+        # which exp(+-g_k) are needed
         need_pos = [False] * N   # exp(+g): species is a net product of a reversible reaction
         need_neg = [False] * N   # exp(-g): net reactant
         for rx in m.reactions:
@@ -181,59 +256,40 @@ class BK1Emitter:
                     elif v < 0:
                         need_neg[k] = True
 
-        # g_k/RT = b0 + b1 lnT + b6/T + T (b2 + T (b3 + T (b4 + T b5)))       (reaction_rates.py:565-569)
-        def gcoef(a):
-            return [a[0] - a[6], -a[0], -a[1] / 2, (1. / 3. - 1. / 2.) * a[2], (1. / 4. - 1. / 3.) * a[3],
-                    (1. / 5. - 1. / 4.) * a[4], a[5]]
-
-        w(f'double EG[{N}], RG[{N}];   // exp(+g_k/RT), exp(-g_k/RT)')
-        for k in range(N):
-            if not (need_pos[k] or need_neg[k]):
-                continue
-            c, lo, hi = self.nasa_select(k, gcoef)
-            # range of g over the validity interval (sampled; polynomial is smooth)
-            gmin, gmax = float('inf'), float('-inf')
-            s = m.species[k]
-            for i in range(200):
-                t = T_VALID_LO + (T_VALID_HI - T_VALID_LO) * i / 199
-                b = gcoef(s.nasa_lo if t <= s.T_mid else s.nasa_hi)
-                g = b[0] + b[1] * math.log(t) + b[6] / t + t * (b[2] + t * (b[3] + t * (b[4] + t * b[5])))
-                gmin, gmax = min(gmin, g), max(gmax, g)
-            w('{')
-            w(f'  const double g = fma(fma(fma(fma({c[5]}, T, {c[4]}), T, {c[3]}), T, {c[2]}), T, '
-              f'fma({c[1]}, lnT, fma({c[6]}, rcpT, {c[0]})));')
-            if need_pos[k]:
-                w(f'  EG[{k}] = {self.exp("g", gmin * 1.05 - 5, gmax * 1.05 + 5)};')
-                if need_neg[k]:
-                    w(f'  RG[{k}] = kx_rcp(EG[{k}]);')
-                    self.stats['rcp'] += 1
-            else:
-                w(f'  RG[{k}] = {self.exp("-g", -gmax * 1.05 - 5, -gmin * 1.05 + 5)};')
-            w('}')
-
-        # ---- third bodies ----
-        w('double Cm = 0.0;')
-        for k in range(N):
-            w(f'Cm += C[{k}];')
-        w(f'const double C0 = {K(const.ONE_ATM / const.R_GAS)} * rcpT;')
-        w(f'const double rcpC0 = {K(const.R_GAS / const.ONE_ATM)} * T;')
-        # distinct efficiency vectors are evaluated once (declared here, at function scope)
+        # ---- pass 1 over the state rows: mean molar mass, density, third-body sums -------------------
+        # (productionRates.okl:11-41).  Cm = sum_k C_k = rho * sum_k Y_k/M_k; an efficiency vector is
+        # Cm + sum_k (eps_k - 1) C_k (reaction_rates.py:298-301); distinct vectors are evaluated once.
         eff_names = {}
         for rx in m.reactions:
             if rx.efficiencies is not None and tuple(rx.efficiencies) not in eff_names:
-                name = f'M{len(eff_names)}'
-                eff_names[tuple(rx.efficiencies)] = name
-                expr = 'Cm'
-                for k, e in enumerate(rx.efficiencies):
-                    if e != 1:
-                        expr = f'fma({K(e - 1)}, C[{k}], {expr})'
-                w(f'const double {name} = {expr};')
+                eff_names[tuple(rx.efficiencies)] = f'M{len(eff_names)}'
+        w('const double T = Tref * kx_ld_stream(state + id);')
+        w('const double rcpT = kx_rcp(T);')
+        w('const double lnT = kx_log(T);')
+        w('double rcpMbar = 0.0;')
+        for name in eff_names.values():
+            w(f'double {name} = 0.0;')
+        w('{')
+        for k in range(N):
+            w(f'  const double w{k} = fmax(0.0, kx_ld_stream(sp + {k} * offset)) * {K(1. / m.species[k].M)}; '
+              f'rcpMbar += w{k};')
+            for vec, name in eff_names.items():
+                if vec[k] != 1:
+                    w(f'  {name} = fma({K(vec[k] - 1)}, w{k}, {name});')
+        w('}')
+        w('const double rho = pressure_R * rcpT * kx_rcp(rcpMbar);')
+        w('const double Cm = rho * rcpMbar;')
+        for name in eff_names.values():
+            w(f'{name} = fma(rho, {name}, Cm);')
+        w(f'const double C0 = {K(const.ONE_ATM / const.R_GAS)} * rcpT;')
+        w(f'const double rcpC0 = {K(const.R_GAS / const.ONE_ATM)} * T;')
+        flag_pos = len(body)
 
         def collider(rx):
             if rx.efficiencies is not None:
                 return eff_names[tuple(rx.efficiencies)]
             if rx.third_body_index >= 0:
-                return f'C[{rx.third_body_index}]'
+                return f'cs{rx.third_body_index}'
             return 'Cm'
 
         # ln(M) once per distinct collider of a Troe reaction whose Pr is formed as exp(.)*M
@@ -243,42 +299,155 @@ class BK1Emitter:
             if rx.kind == 'Troe':
                 name = collider(rx)
                 arg, _ = self.ratio_expr(rx)
-                if arg is not None and not name.startswith('C[') and name not in ln_collider:
-                    v = 'ln_' + name
-                    w(f'const double {v} = kx_log(fmax({name}, 1e-300));')
-                    self.stats['log'] += 1
-                    ln_collider[name] = v
+                if not name.startswith('cs'):
+                    if arg is not None and name not in ln_collider:
+                        v = 'ln_' + name
+                        w(f'const double {v} = kx_log(fmax({name}, 1e-300));')
+                        self.stats['log'] += 1
+                        ln_collider[name] = v
 
-        def ln_of(name):
-            return ln_collider[name]
+        # ---- per-species live state --------------------------------------------------------------
+        used = sorted(first)                                  # species that occur in some reaction
+        w('double ' + ', '.join(f'cs{k}' for k in used) + ';')
+        w('double ' + ', '.join(f'wd{k}' for k in used) + ';')
+        if not ring:
+            w('double ' + ', '.join(f'y{k}' for k in used) + ';')
+        w('double hsum = 0.0;')
+        self.eg_slot, self.rg_slot = {}, {}
+        free_slots, n_slots = [], 0
+        act_order = sorted(used, key=lambda k: (first[k], k))      # activation order
+        rank = {k: i for i, k in enumerate(act_order)}
+        if ring:
+            n_slots = ring                                          # slots [0, ring) = the Y ring
+        if gibbs_in_smem or ring:
+            w('extern __shared__ double kx_sm[];')
+            w('double* const gs = kx_sm + threadIdx.x;')
+        if ring:
+            w('const unsigned ring_base = (unsigned)__cvta_generic_to_shared(gs);')
+            for k in act_order[:ring]:
+                w(f'kx_cp_async8(ring_base + {rank[k] % ring} * {block} * 8, sp + {k} * offset);')
+        if not gibbs_in_smem:
+            names = [f'eg{k}' for k in used if need_pos[k]] + [f'rg{k}' for k in used if need_neg[k]]
+            if names:
+                w('double ' + ', '.join(names) + ';')
 
-        w(f'double wd[{N}];')
-        for k in range(N):
-            w(f'wd[{k}] = 0.0;')
+        def take_slot():
+            nonlocal n_slots
+            if free_slots:
+                return free_slots.pop(0)
+            n_slots += 1
+            return n_slots - 1
 
-        # ---- reactions, grouped by shared (beta, Ta) of the main rate constant ----
-        groups = {}
-        for i, rx in enumerate(m.reactions):
-            if rx.kind == 'P-log':
-                key = ('plog', i)
+        def gcoef(a):   # g/RT = b0 + b1 lnT + b6/T + T (b2 + T (b3 + T (b4 + T b5)))   (reaction_rates.py:565-569)
+            return [a[0] - a[6], -a[0], -a[1] / 2, (1. / 3. - 1. / 2.) * a[2], (1. / 4. - 1. / 3.) * a[3],
+                    (1. / 5. - 1. / 4.) * a[4], a[5]]
+
+        def hcoef(a):   # h/RT (thermodynamics.py:74-75)
+            return [a[0], a[1] / 2, a[2] / 3, a[3] / 4, a[4] / 5, a[5]]
+
+        def activate(k):
+            """species k becomes live: concentration, zeroed accumulator, exp(+-g_k/RT)"""
+            if ring:
+                r = rank[k]
+                pending = max(0, min(ring - 1, len(act_order) - 1 - r))
+                w(f'kx_cp_async_wait<{pending}>();')
+                w(f'const double y{k} = gs[{r % ring} * {block}];')
+                if r + ring < len(act_order):
+                    nk = act_order[r + ring]
+                    w(f'kx_cp_async8(ring_base + {r % ring} * {block} * 8, sp + {nk} * offset);')
+            if not ring and pin_loads:
+                # volatile max: keeps this activation ordered after the loads issued `prefetch` activations
+                # ahead (volatile asms are not reordered among themselves), so the compiler cannot sink those
+                # loads down to their first use
+                w(f'{{ double t; asm volatile("max.f64 %0, %1, 0d0000000000000000;" : "=d"(t) : "d"(y{k})); '
+                  f'cs{k} = t * ({K(1. / m.species[k].M)} * rho); wd{k} = 0.0; }}')
             else:
-                b, Ta = rx.rate.b, rx.rate.Ta
-                trivial = (b == 0 and Ta == 0) or (Ta == 0 and b in (-2, -1, 1, 2))
-                key = (b, Ta, i) if trivial else (b, Ta)
-            groups.setdefault(key, []).append(i)
+                w(f'cs{k} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); wd{k} = 0.0;')
+            if not (need_pos[k] or need_neg[k]):
+                return
+            c, _, _ = self.nasa_select(k, gcoef)
+            s = m.species[k]
+            gmin, gmax = float('inf'), float('-inf')
+            for i in range(200):
+                t = T_VALID_LO + (T_VALID_HI - T_VALID_LO) * i / 199
+                b = gcoef(s.nasa_lo if t <= s.T_mid else s.nasa_hi)
+                g = b[0] + b[1] * math.log(t) + b[6] / t + t * (b[2] + t * (b[3] + t * (b[4] + t * b[5])))
+                gmin, gmax = min(gmin, g), max(gmax, g)
+            glo, ghi = min(gmin * 1.05, gmin * 0.95) - 5, max(gmax * 1.05, gmax * 0.95) + 5
+            if need_pos[k]:
+                self.eg_slot[k] = take_slot() if gibbs_in_smem else None
+            if need_neg[k]:
+                self.rg_slot[k] = take_slot() if gibbs_in_smem else None
+            w('{')
+            w(f'  const double g = fma(fma(fma(fma({c[5]}, T, {c[4]}), T, {c[3]}), T, {c[2]}), T, '
+              f'fma({c[1]}, lnT, fma({c[6]}, rcpT, {c[0]})));')
+            if need_pos[k]:
+                w(f'  const double e = {self.exp("g", glo, ghi)};')
+                w(f'  {self.EG(k)} = e;')
+                if need_neg[k]:
+                    w(f'  {self.RG(k)} = kx_rcp(e);')
+                    self.stats['rcp'] += 1
+            else:
+                w(f'  {self.RG(k)} = {self.exp("-g", -ghi, -glo)};')
+            w('}')
+
+        def retire(k):
+            """last use of species k is behind us: write its rate row, add its heat release, free its slots
+            (productionRates.okl:48-62)"""
+            c, _, _ = self.nasa_select(k, hcoef)
+            w(f'if (live) kx_st_stream(out + {k} * offset, {K(m.species[k].M)} * wd{k});')
+            w(f'hsum = fma(wd{k}, fma(fma(fma(fma({c[4]}, T, {c[3]}), T, {c[2]}), T, {c[1]}), T, '
+              f'fma({c[5]}, rcpT, {c[0]})), hsum);')
+            for slots in (self.eg_slot, self.rg_slot):
+                if gibbs_in_smem and k in slots:
+                    free_slots.append(slots[k])
 
         def conc_product(nu):
             terms = []
             for k, c in enumerate(nu):
-                terms += [f'C[{k}]'] * c
+                terms += [f'cs{k}'] * c
             return ' * '.join(terms)
 
-        for gi, (key, members) in enumerate(groups.items()):
-            first = m.reactions[members[0]]
-            w(f'// ---- rate-constant group {gi}: ' + '; '.join(str(i + 1) for i in members))
+        # species that never occur in a reaction: rate row is zero (the reference's wdot[k] stays 0)
+        for k in range(N):
+            if k not in first:
+                w(f'if (live) kx_st_stream(out + {k} * offset, 0.0);')
+
+        # ---- units in schedule order ---------------------------------------------------------------
+        by_first = {}
+        for k, pos in first.items():
+            by_first.setdefault(pos, []).append(k)
+        by_last = {}
+        for k, pos in last.items():
+            by_last.setdefault(pos, []).append(k)
+        loaded = set()
+
+        def issue_loads(upto_rank):
+            if ring:
+                return
+            for k in act_order[:upto_rank + 1]:
+                if k not in loaded:
+                    loaded.add(k)
+                    w(f'y{k} = kx_ld_stream(sp + {k} * offset);')
+
+        emitted = 0
+        peak_live, live_now = 0, 0
+        for pos, ui in enumerate(order):
+            members = units[ui]
+            for k in sorted(by_first.get(pos, [])):
+                issue_loads(rank[k] + prefetch)
+                activate(k)
+                live_now += 1
+            peak_live = max(peak_live, live_now)
+            if sync_every and emitted and emitted // sync_every != (emitted + len(members)) // sync_every:
+                w('__syncthreads();')
+            emitted += len(members)
+            first_rx = m.reactions[members[0]]
+            w(f'// ---- unit {pos}: reactions ' + ', '.join(str(i + 1) for i in members))
             w('{')
-            if first.kind != 'P-log':
-                w(f'  const double kbase = {self.arrhenius_group_expr(first.rate.A, first.rate.b, first.rate.Ta)};')
+            if first_rx.kind != 'P-log':
+                w(f'  const double kbase = '
+                  f'{self.arrhenius_group_expr(first_rx.rate.A, first_rx.rate.b, first_rx.rate.Ta)};')
             for i in members:
                 rx = m.reactions[i]
                 w(f'  // {i + 1}: {rx.equation}')
@@ -288,7 +457,7 @@ class BK1Emitter:
                 elif i == members[0]:
                     w('    double kf = kbase;')
                 else:
-                    w(f'    double kf = kbase * {K(rx.rate.A / first.rate.A)};')
+                    w(f'    double kf = kbase * {K(rx.rate.A / first_rx.rate.A)};')
 
                 if rx.kind == 'three-body':
                     w(f'    kf *= {collider(rx)};')
@@ -307,8 +476,8 @@ class BK1Emitter:
                     elif rx.kind == 'Troe':
                         # log10(Pr + CFLOAT_MIN): from the exponent and ln(M) when M is a sum of
                         # concentrations; literally when the collider is a single species (can be 0)
-                        if arg is not None and not M.startswith('C['):
-                            w(f'    const double logPr = (lnr + {ln_of(M)}) * {K(1 / math.log(10))};')
+                        if arg is not None and M in ln_collider:
+                            w(f'    const double logPr = (lnr + {ln_collider[M]}) * {K(1 / math.log(10))};')
                         else:
                             w('    const double logPr = kx_log10(Pr + 1e-300);')
                             self.stats['log'] += 1
@@ -325,13 +494,13 @@ class BK1Emitter:
                         self.stats['rcp'] += 1
                         w('    kf *= Pr * rcp1Pr * F;')
                     else:  # SRI (reaction_rates.py:346-357)
-                        s = rx.sri
+                        sr = rx.sri
                         w('    const double logPr = kx_log10(Pr);')
-                        w(f'    const double sb = {K(s["A"])} * kx_exp_wide({K(-s["B"])} * rcpT) + '
-                          f'kx_exp_wide({K(-1. / (s["C"] + const.FLOAT_MIN))} * T);')
-                        w(f'    double F = {K(s["D"])} * kx_pow(sb, kx_rcp(fma(logPr, logPr, 1.0)));')
-                        if s['E'] != 0:
-                            w(f'    F *= kx_exp({K(s["E"])} * lnT);')
+                        w(f'    const double sb = {K(sr["A"])} * kx_exp_wide({K(-sr["B"])} * rcpT) + '
+                          f'kx_exp_wide({K(-1. / (sr["C"] + const.FLOAT_MIN))} * T);')
+                        w(f'    double F = {K(sr["D"])} * kx_pow(sb, kx_rcp(fma(logPr, logPr, 1.0)));')
+                        if sr['E'] != 0:
+                            w(f'    F *= kx_exp({K(sr["E"])} * lnT);')
                         self.stats['log'] += 2
                         self.stats['exp'] += 3
                         w('    kf *= Pr * rcp1Pr * F;')
@@ -343,14 +512,14 @@ class BK1Emitter:
                 else:
                     # 1/Kc = prod exp(g)^nu * C0^(-sum nu); interleave +g / -g factors so partial
                     # products stay O(exp(delta g)) (no intermediate over/underflow)
-                    pos = [f'EG[{k}]' for k, v in enumerate(net) if v > 0 for _ in range(v)]
-                    neg = [f'RG[{k}]' for k, v in enumerate(net) if v < 0 for _ in range(-v)]
+                    pos_f = [self.EG(k) for k, v in enumerate(net) if v > 0 for _ in range(v)]
+                    neg_f = [self.RG(k) for k, v in enumerate(net) if v < 0 for _ in range(-v)]
                     factors = []
-                    while pos or neg:
-                        if pos:
-                            factors.append(pos.pop(0))
-                        if neg:
-                            factors.append(neg.pop(0))
+                    while pos_f or neg_f:
+                        if pos_f:
+                            factors.append(pos_f.pop(0))
+                        if neg_f:
+                            factors.append(neg_f.pop(0))
                     sn = sum(net)
                     factors += ['C0' if sn < 0 else 'rcpC0'] * abs(sn)
                     w(f'    const double kr = {" * ".join(factors)};')
@@ -358,39 +527,34 @@ class BK1Emitter:
                     w(f'    const double q = kf * fma(-kr, {Rr}, {Rf});')
                 for k, v in enumerate(net):
                     if v == 1:
-                        w(f'    wd[{k}] += q;')
+                        w(f'    wd{k} += q;')
                     elif v == -1:
-                        w(f'    wd[{k}] -= q;')
+                        w(f'    wd{k} -= q;')
                     elif v != 0:
-                        w(f'    wd[{k}] = fma({float(v)}, q, wd[{k}]);')
+                        w(f'    wd{k} = fma({float(v)}, q, wd{k});')
                 w('  }')
             w('}')
+            for k in sorted(by_last.get(pos, [])):
+                retire(k)
+                live_now -= 1
+        w(f'if (live) kx_st_stream(rates + id, {K(-const.R_GAS)} * T * hsum);')
 
-        # ---- outputs (productionRates.okl:48-62) ----
-        def hcoef(a):
-            return [a[0], a[1] / 2, a[2] / 3, a[3] / 4, a[4] / 5, a[5]]
-
-        w('double hsum = 0.0;')
-        for k in range(N):
-            c, _, _ = self.nasa_select(k, hcoef)
-            w(f'kx_st_stream(out + {k} * offset, {K(m.species[k].M)} * wd[{k}]);')
-            w(f'hsum = fma(wd[{k}], fma(fma(fma(fma({c[4]}, T, {c[3]}), T, {c[2]}), T, {c[1]}), T, '
-              f'fma({c[5]}, rcpT, {c[0]})), hsum);')
-        w(f'kx_st_stream(rates + id, {K(-const.R_GAS)} * T * hsum);')
-
+        self.smem_doubles_per_thread = n_slots if (gibbs_in_smem or ring) else 0
+        self.schedule_stats.update(peak_live=peak_live, smem_slots=n_slots)
         body[flag_pos:flag_pos] = ['  ' + v for v in self._flags.values()]
 
         head = [
             f'// BK1 (species production rates): {m.name}, {N} species / {m.n_reactions} reactions; '
             f'{self.stats["exp"]} kx_exp, {self.stats["exp_wide"]} wide exp, {self.stats["log"]} log, '
-            f'{self.stats["rcp"]} rcp per state',
+            f'{self.stats["rcp"]} rcp per state; peak live species {peak_live}, {n_slots} smem slots',
             f'extern "C" __global__ void __launch_bounds__({block}, {min_blocks})',
             f'{kernel_name}(const long long n_states, const long long offsetT, const long long offset,',
             '           const double pressure_R, const double P, const double lnP,',
             '           const double* __restrict__ state, double* __restrict__ rates, const double Tref)',
             '{',
-            '  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;',
-            '  if (id >= n_states) return;',
+            '  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;',
+            '  const bool live = gid < n_states;',
+            '  const long long id = live ? gid : n_states - 1;   // tail threads recompute the last state, store nothing',
             '  const double* sp = state + id + offsetT;',
             '  double* out = rates + id + offsetT;',
         ]

@@ -8,58 +8,106 @@
 // sm_100a, needs 73 KB of spill traffic per state and ~19k MOVs for its FP64 immediates):
 //   * per-state vectors X_k and the running sums live in shared memory as [k][thread] (conflict-free,
 //     one 8-byte word per lane), NOT in per-thread local memory;
-//   * the N(N-1)/2 binary-diffusion polynomials and the N^2 Wilke mass factors are TABLES (global memory,
-//     L2 resident, read with warp-uniform 128-bit loads), walked by a small register-tiled loop nest:
-//     TB x TB species tiles, accumulators for both the row block and the column block in registers
-//     (each D_jk is evaluated once and used for S_j and S_k);  code size is a few KB -> I-cache resident;
+//   * the N(N-1)/2 binary-diffusion polynomials and the N^2 Wilke mass factors are TABLES in global
+//     memory (L2 resident).  They are cut into chunks (one k-block of Wilke factors / one TB x TB tile
+//     of diffusion quartics) that the CTA streams through a double buffer in shared memory with TMA
+//     bulk copies (cp.async.bulk + mbarrier complete_tx): chunk c+2 is in flight while the warps work
+//     on chunk c, and every coefficient read in the inner loops is a conflict-free shared-memory
+//     broadcast instead of a global load (v1 of this kernel read the tables with __ldg and spent 2.0
+//     stall cycles per issue slot on the long scoreboard);
+//   * the loop nest over TB x TB species tiles keeps the accumulators of both the row block and the
+//     column block in registers (each D_jk is evaluated once and used for S_j and S_k); the code is a
+//     few KB and instruction-cache resident;
 //   * Wilke's sum is refactored:  (C1 + C2 v_k/v_j)^2 = c_kj (1 + w_k/w_j)^2 with w = v M^(-1/4) and
 //     c_kj = 1/sqrt(8 (1 + M_k/M_j)), so
 //        Phi_k = sum_j c_kj X_j  + 2 w_k sum_j c_kj X_j/w_j  + w_k^2 sum_j c_kj X_j/w_j^2
-//     i.e. three constant-matrix x per-state-vector products: 3 N^2 DFMA instead of 4 N^2 mixed ops;
-//   * divisions are MUFU.RCP64H + Newton (kx_rcp), rho*D_km is simplified algebraically (p and Mbar
-//     cancel exactly as in the reference's formula, transportProps.okl:41-46).
+//     i.e. three constant-matrix x per-state-vector products: 3 N^2 DFMA instead of 4 N^2 mixed ops.
+//     (DMMA was measured to share the FP64 pipe with DFMA on B200 -- profiles/peaks_r01.json -- so the
+//     products stay on the vector pipe);
+//   * divisions are MUFU.RCP64H + one cubic Newton step (kx_rcp), rho*D_km is simplified algebraically
+//     (p and Mbar cancel exactly as in the reference's formula, transportProps.okl:41-46).
 //
 // The including translation unit (generated per mechanism) defines:
-//   KX_N, KX_NP (= KX_N rounded up to a multiple of KX_TB), KX_TB, KX_BK2_BLOCK, KX_BK2_MINB
+//   KX_N, KX_NP (= KX_N rounded up to a multiple of KX_TB), KX_TB, KX_BK2_BLOCK, KX_BK2_MINB,
+//   KX_WCHUNK (doubles per Wilke chunk, even), KX_DCHUNK (= KX_TB*KX_TB*6)
 //   __constant__ double kx_rcpM[KX_N], kx_M[KX_N], kx_m4[KX_N]  (1/M_k, M_k, M_k^(-1/4))
 //   __constant__ double kx_cond[KX_N][5], kx_visc[KX_N][5]       quartics in ln T
-//   __device__   double kx_wilke[KX_NP/KX_TB][KX_N][KX_TB]        c_kj, k-block major
-//   __device__   double kx_diff[n_tiles][KX_TB*KX_TB][6]          lower-triangular tiles (kb >= jb),
+//   __device__   double kx_wilke[KX_NB][KX_WCHUNK]                c_kj as [kb][j][i], k = kb*TB + i
+//   __device__   double kx_diff[n_tiles][KX_DCHUNK]               lower-triangular tiles (kb >= jb),
 //                                                                 row-major over (kb, jb); 5 coefs + pad
 #pragma once
+#include <cstdint>
 #include "kx_math.cuh"
 
 #define KX_NB (KX_NP / KX_TB)
+#define KX_CHUNK_MAX (KX_WCHUNK > KX_DCHUNK ? KX_WCHUNK : KX_DCHUNK)
+#define KX_N_DTILES (KX_NB * (KX_NB + 1) / 2)
 
 KX_DEVICE double kx_quartic(const double* __restrict__ c, double l)
 {
   return fma(fma(fma(fma(c[4], l, c[3]), l, c[2]), l, c[1]), l, c[0]);
 }
 
-// 5 coefficients stored as 6 doubles, fetched with three 128-bit warp-uniform loads
-KX_DEVICE double kx_quartic6(const double2* __restrict__ c, double l)
+// ---- TMA bulk copy + mbarrier plumbing -----------------------------------------------------------
+KX_DEVICE void kx_mbar_init(uint64_t* bar, unsigned count)
 {
-  const double2 a = __ldg(c), b = __ldg(c + 1), d = __ldg(c + 2);
-  return fma(fma(fma(fma(d.x, l, b.y), l, b.x), l, a.y), l, a.x);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
 }
+KX_DEVICE void kx_bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
+{
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(b)
+               : "memory");
+}
+KX_DEVICE void kx_mbar_wait(uint64_t* bar, unsigned parity)
+{
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "KX_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra KX_DONE_%=;\n\t"
+      "bra KX_WAIT_%=;\n\t"
+      "KX_DONE_%=:\n\t}" ::"r"(b), "r"(parity)
+      : "memory");
+}
+
+// chunk stream: chunks 0..KX_NB-1 are the Wilke k-blocks, then the KX_N_DTILES diffusion tiles
+KX_DEVICE const double* kx_chunk_src(int c)
+{
+  return c < KX_NB ? kx_wilke + (size_t)c * KX_WCHUNK : kx_diff + (size_t)(c - KX_NB) * KX_DCHUNK;
+}
+KX_DEVICE unsigned kx_chunk_bytes(int c) { return (c < KX_NB ? KX_WCHUNK : KX_DCHUNK) * 8u; }
 
 extern "C" __global__ void __launch_bounds__(KX_BK2_BLOCK, KX_BK2_MINB)
 kx_bk2_f64(const long long n_states, const long long offsetT, const long long offset, const double pressure,
            const double* __restrict__ state, double* __restrict__ conductivity,
            double* __restrict__ viscosity, double* __restrict__ rhoD, const double Tref)
 {
-  extern __shared__ double kx_sm[];
-  double* __restrict__ X = kx_sm + threadIdx.x;                          // X[k] at X[k * BLOCK]
-  double* __restrict__ S = kx_sm + KX_NP * KX_BK2_BLOCK + threadIdx.x;   // b_k = 1/w_k, later the sums S_k
+  extern __shared__ __align__(16) double kx_sm[];
   constexpr int LD = KX_BK2_BLOCK;
+  constexpr int N_CHUNKS = KX_NB + KX_N_DTILES;
+  double* const buf0 = kx_sm;                                   // 2 x KX_CHUNK_MAX doubles
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(kx_sm + 2 * KX_CHUNK_MAX);   // 2 mbarriers
+  double* __restrict__ X = kx_sm + 2 * KX_CHUNK_MAX + 2 + threadIdx.x;           // X[k] at X[k * LD]
+  double* __restrict__ S = X + KX_NP * LD;                      // b_k = 1/w_k, later the sums S_k
 
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = gid < n_states;
   const long long id = live ? gid : n_states - 1;   // tail threads recompute the last state, store nothing
 
+  if (threadIdx.x == 0) {
+    kx_mbar_init(&bars[0], 1);
+    kx_mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    kx_bulk_load(buf0, kx_chunk_src(0), kx_chunk_bytes(0), &bars[0]);
+    if (N_CHUNKS > 1) kx_bulk_load(buf0 + KX_CHUNK_MAX, kx_chunk_src(1), kx_chunk_bytes(1), &bars[1]);
+  }
+
   const double T = Tref * kx_ld_stream(state + id);
   const double lnT = kx_log(T);
-  const double rcpT = kx_rcp(T);
   const double sqrT = sqrt(T);
 
   // ---- mole fractions (transportProps.okl:23-35) ----
@@ -91,6 +139,19 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
     for (int k = KX_N; k < KX_NP; k++) { X[k * LD] = 0.0; S[k * LD] = 1.0; }
     if (live) kx_st_stream(conductivity + id, sqrT * (0.5 * (s1 + kx_rcp(s2))));
   }
+  __syncthreads();   // mbarrier inits visible to all threads before the first wait
+
+  int chunk = 0;
+  // release the buffer of the chunk just consumed and refill it with chunk+2
+  auto advance = [&]() {
+    __syncthreads();
+    if (threadIdx.x == 0 && chunk + 2 < N_CHUNKS) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      kx_bulk_load(buf0 + (chunk & 1) * KX_CHUNK_MAX, kx_chunk_src(chunk + 2), kx_chunk_bytes(chunk + 2),
+                   &bars[chunk & 1]);
+    }
+    chunk++;
+  };
 
   // ---- viscosity: Wilke with the three-matvec refactoring ----
   {
@@ -99,14 +160,15 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
       double a0[KX_TB], a1[KX_TB], a2[KX_TB];
 #pragma unroll
       for (int i = 0; i < KX_TB; i++) a0[i] = a1[i] = a2[i] = 0.0;
-      const double* __restrict__ cw = kx_wilke + (size_t)kb * KX_N * KX_TB;
+      kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
+      const double* __restrict__ cw = buf0 + (chunk & 1) * KX_CHUNK_MAX;
 #pragma unroll 2
       for (int j = 0; j < KX_N; j++) {
         const double x = X[j * LD], b = S[j * LD];
         const double xb = x * b, xbb = xb * b;
 #pragma unroll
         for (int i = 0; i < KX_TB; i++) {
-          const double c = __ldg(cw + j * KX_TB + i);
+          const double c = cw[j * KX_TB + i];
           a0[i] = fma(c, x, a0[i]);
           a1[i] = fma(c, xb, a1[i]);
           a2[i] = fma(c, xbb, a2[i]);
@@ -122,49 +184,59 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
           vis = fma(X[k * LD] * (v * v), kx_rcp(phi), vis);
         }
       }
+      advance();
     }
     if (live) kx_st_stream(viscosity + id, sqrT * vis);
   }
 
   // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj, tiles of the lower triangle ----
   for (int k = 0; k < KX_NP; k++) S[k * LD] = 0.0;
-  {
-    const double2* __restrict__ tile = reinterpret_cast<const double2*>(kx_diff);
-    for (int kb = 0; kb < KX_NB; kb++) {
-      double xk[KX_TB], sk[KX_TB];
+  for (int kb = 0; kb < KX_NB; kb++) {
+    double xk[KX_TB], sk[KX_TB];
 #pragma unroll
-      for (int i = 0; i < KX_TB; i++) { xk[i] = X[(kb * KX_TB + i) * LD]; sk[i] = 0.0; }
-      for (int jb = 0; jb < kb; jb++) {
-        double xj[KX_TB], sj[KX_TB];
+    for (int i = 0; i < KX_TB; i++) { xk[i] = X[(kb * KX_TB + i) * LD]; sk[i] = 0.0; }
+    for (int jb = 0; jb < kb; jb++) {
+      double xj[KX_TB], sj[KX_TB];
 #pragma unroll
-        for (int i = 0; i < KX_TB; i++) { xj[i] = X[(jb * KX_TB + i) * LD]; sj[i] = 0.0; }
+      for (int i = 0; i < KX_TB; i++) { xj[i] = X[(jb * KX_TB + i) * LD]; sj[i] = 0.0; }
+      kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
+      const double2* __restrict__ tile = reinterpret_cast<const double2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
 #pragma unroll
-        for (int i = 0; i < KX_TB; i++) {
+      for (int i = 0; i < KX_TB; i++) {
 #pragma unroll
-          for (int j = 0; j < KX_TB; j++) {
-            const double d = kx_rcp(kx_quartic6(tile + (i * KX_TB + j) * 3, lnT));
-            sk[i] = fma(xj[j], d, sk[i]);
-            sj[j] = fma(xk[i], d, sj[j]);
-          }
+        for (int j = 0; j < KX_TB; j++) {
+          const double2* c = tile + (i * KX_TB + j) * 3;
+          const double2 c01 = c[0], c23 = c[1], c4 = c[2];
+          const double p = fma(fma(fma(fma(c4.x, lnT, c23.y), lnT, c23.x), lnT, c01.y), lnT, c01.x);
+          const double d = kx_rcp(p);
+          sk[i] = fma(xj[j], d, sk[i]);
+          sj[j] = fma(xk[i], d, sj[j]);
         }
-#pragma unroll
-        for (int i = 0; i < KX_TB; i++) S[(jb * KX_TB + i) * LD] += sj[i];
-        tile += KX_TB * KX_TB * 3;
       }
-      // diagonal tile: pairs i > j inside the block
+#pragma unroll
+      for (int i = 0; i < KX_TB; i++) S[(jb * KX_TB + i) * LD] += sj[i];
+      advance();
+    }
+    // diagonal tile: pairs i > j inside the block
+    kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
+    {
+      const double2* __restrict__ tile = reinterpret_cast<const double2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
 #pragma unroll
       for (int i = 1; i < KX_TB; i++) {
 #pragma unroll
         for (int j = 0; j < i; j++) {
-          const double d = kx_rcp(kx_quartic6(tile + (i * KX_TB + j) * 3, lnT));
+          const double2* c = tile + (i * KX_TB + j) * 3;
+          const double2 c01 = c[0], c23 = c[1], c4 = c[2];
+          const double p = fma(fma(fma(fma(c4.x, lnT, c23.y), lnT, c23.x), lnT, c01.y), lnT, c01.x);
+          const double d = kx_rcp(p);
           sk[i] = fma(xk[j], d, sk[i]);
           sk[j] = fma(xk[i], d, sk[j]);
         }
       }
-      tile += KX_TB * KX_TB * 3;
-#pragma unroll
-      for (int i = 0; i < KX_TB; i++) S[(kb * KX_TB + i) * LD] += sk[i];
     }
+#pragma unroll
+    for (int i = 0; i < KX_TB; i++) S[(kb * KX_TB + i) * LD] += sk[i];
+    advance();
   }
 
   // ---- rho * D_km  (mix_transport.py:621-622 and transportProps.okl:43-47; p and Mbar cancel) ----
@@ -177,5 +249,5 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
       kx_st_stream(out + k * offset, f * num * kx_rcp(S[k * LD]));
     }
   }
-  (void)pressure; (void)rcpT;
+  (void)pressure;
 }

@@ -8,7 +8,7 @@
 //
 //     kx_exp   15 FP64  (Cody-Waite reduction + degree-11 polynomial, exponent patched with integer ops)
 //     kx_log   ~17 FP64 (atanh series in s=(m-1)/(m+1), reciprocal by MUFU.RCP64H + Newton)
-//     kx_rcp    5 FP64 + 1 MUFU
+//     kx_rcp    3 FP64 + 1 MUFU
 //
 // The reference relies on the backend's libm for these (benchmark/src/kinetix.cpp:246-251 maps
 // __KINETIX_EXP__/LOG__/LOG10__/POW__ onto exp/log/log10/pow); parity is to 1e-10, not bit-wise.
@@ -18,7 +18,8 @@
 #define KX_DEVICE __device__ __forceinline__
 
 // ---- reciprocal ------------------------------------------------------------------------------
-// MUFU.RCP64H seed + (cubic, then quadratic) Newton steps: error e0^6, no range checks.
+// MUFU.RCP64H seed (measured max relative error 9.9e-7 on B200, profiles/peaks_r01.json) + one cubic
+// Newton step: error e0^3 ~ 1e-18, measured 1.1e-16 (= rounding).  3 DFMA + 1 MUFU, no range checks.
 // Valid for normal, finite, non-zero |a| in about [1e-300, 1e300] -- all uses satisfy this.
 KX_DEVICE double kx_rcp(double a)
 {
@@ -26,10 +27,7 @@ KX_DEVICE double kx_rcp(double a)
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
   double e = fma(-a, x, 1.0);
   e = fma(e, e, e);
-  x = fma(x, e, x);
-  e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  return x;
+  return fma(x, e, x);
 }
 
 // a / b with the reciprocal above (one extra DMUL); relative error ~2e-16.
@@ -61,6 +59,31 @@ KX_DEVICE double kx_exp(double x)
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   k = max(min(k, 1022), -1021);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// exp(x) for arguments the emitter has PROVEN to lie in [-690, 690] for every valid state: no exponent
+// clamp at all (14 FP64 + 3 integer instructions).
+KX_DEVICE double kx_exp_nc(double x)
+{
+  const double MAGIC = 6755399441055744.0;
+  double kd = fma(x, 1.4426950408889634, MAGIC);
+  const int k = __double2loint(kd);
+  kd -= MAGIC;
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = 2.5110037605963777e-08;
+  p = fma(p, r, 2.763263963904103e-07);
+  p = fma(p, r, 2.755724091857897e-06);
+  p = fma(p, r, 2.4801485482328494e-05);
+  p = fma(p, r, 0.00019841269890047113);
+  p = fma(p, r, 0.0013888888952314775);
+  p = fma(p, r, 0.008333333333319601);
+  p = fma(p, r, 0.0416666666664881);
+  p = fma(p, r, 0.1666666666666668);
+  p = fma(p, r, 0.5000000000000019);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
@@ -111,4 +134,18 @@ KX_DEVICE double kx_ld_stream(const double* p)
 KX_DEVICE void kx_st_stream(double* p, double v)
 {
   asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// ---- asynchronous 8-byte global -> shared copy (LDGSTS) with FIFO completion ----------------------
+// One commit group per copy; kx_cp_async_wait<N>() returns when all but the N most recent groups of
+// this thread have landed.
+KX_DEVICE void kx_cp_async8(unsigned smem_addr, const double* gptr)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n\tcp.async.commit_group;" ::"r"(smem_addr), "l"(gptr)
+               : "memory");
+}
+template <int N>
+KX_DEVICE void kx_cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }

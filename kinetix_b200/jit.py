@@ -84,7 +84,8 @@ def build_host_library(force=False):
 
 
 def ensure_module(mechanism_path, output_dir=None, fit_rcp_diff=False, single_precision=False, block_size=0,
-                  transport=True, force=False, verbose=False, compile_module=True, extra_nvcc=()):
+                  transport=True, force=False, verbose=False, compile_module=True, extra_nvcc=(),
+                  emit_options=None):
     """Generate (and compile) the sm_100a module for one mechanism; returns the module directory."""
     from .core.emit_module import emit_module
     from .core.mechanism import load_mechanism, mechanism_to_dict
@@ -95,7 +96,8 @@ def ensure_module(mechanism_path, output_dir=None, fit_rcp_diff=False, single_pr
                                                                  block_size))
     lib = os.path.join(out, 'libkx_mech.so')
     opts = dict(fit_rcp_diff=bool(fit_rcp_diff), single_precision=bool(single_precision),
-                block_size=int(block_size or 0), transport=bool(transport), extra_nvcc=list(extra_nvcc))
+                block_size=int(block_size or 0), transport=bool(transport), extra_nvcc=list(extra_nvcc),
+                emit_options=dict(emit_options or {}))
     digest = _hash_files(_emitter_sources() + [mechanism_path], json.dumps(opts, sort_keys=True))
     stamp = os.path.join(out, '.hash')
     fresh = os.path.exists(stamp) and open(stamp).read() == digest
@@ -108,6 +110,7 @@ def ensure_module(mechanism_path, output_dir=None, fit_rcp_diff=False, single_pr
     options = {}
     if block_size:
         options.update(block_bk1=int(block_size), block_bk2=int(block_size))
+    options.update(emit_options or {})
     src, stats = emit_module(mech, fits, options)
     cu = os.path.join(out, 'kx_mech.cu')
     with open(cu, 'w') as fh:

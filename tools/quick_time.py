@@ -16,6 +16,8 @@ ap.add_argument('--mech', default='gri30')
 ap.add_argument('--n', type=int, default=1 << 22)
 ap.add_argument('--reps', type=int, default=5)
 ap.add_argument('--cache', default=None)
+ap.add_argument('--check', action='store_true')
+ap.add_argument('--tag', default='')
 a = ap.parse_args()
 kinetix.init(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', a.mech + '.yaml'), cache_dir=a.cache)
 N = kinetix.nSpecies()
@@ -44,5 +46,17 @@ def timeit(fn):
 t1 = timeit(lambda: kinetix.productionRates(S, S, S, 1.0, st, rates))
 t2 = timeit(lambda: kinetix.mixtureAvgTransportProps(S, S, S, 1.0, st, visc, cond, rhoD))
 t3 = timeit(lambda: kinetix.thermodynamicProps(S, S, S, 1.0, st, visc, rhoD, cond))
-print(f'{a.mech} S={S}: BK1 {t1:.3f} ms = {S / t1 / 1e6:.1f} Mstates/s | BK2 {t2:.3f} ms = {S / t2 / 1e6:.1f} Mstates/s | '
-      f'thermo {t3:.3f} ms = {S / t3 / 1e6:.1f} Mstates/s ({(2 * N + 3) * 8 * S / t3 / 1e6:.0f} GB/s)')
+kinetix.mixtureAvgTransportProps(S, S, S, 1.0, st, visc, cond, rhoD)
+torch.cuda.synchronize()
+msg = ''
+if a.check:
+    from tests.common import Oracle, bk1_errors, rel_err
+    n = 4096
+    orc = Oracle(a.mech)
+    ref = orc.production_rates(base[:, :n].cpu().numpy(), 101325.0)
+    e1 = bk1_errors(rates[:, :n].cpu().numpy(), ref)
+    rc, rv, rrd = orc.transport(base[:, :n].cpu().numpy(), 1.0)
+    e2 = max(rel_err(cond[:n].cpu().numpy(), rc), rel_err(visc[:n].cpu().numpy(), rv), rel_err(rhoD[:, :n].cpu().numpy(), rrd))
+    msg = f' | err bk1 {e1[0]:.1e}/{e1[1]:.1e} bk2 {e2:.1e}'
+print(f'{a.tag} {a.mech} S={S}: BK1 {t1:.3f} ms = {S / t1 / 1e3:.1f} Mstates/s | BK2 {t2:.3f} ms = {S / t2 / 1e3:.1f} Mstates/s | '
+      f'thermo {t3:.3f} ms = {S / t3 / 1e3:.1f} Mstates/s ({(2 * N + 3) * 8 * S / t3 / 1e6:.0f} GB/s){msg}')
