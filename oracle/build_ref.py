@@ -30,7 +30,8 @@ REF = '/root/reference'
 OUT = os.path.join(HERE, '_ref')
 
 DEFAULT = [('gri30', 'parity'), ('gri30', 'serial'), ('gri30', 'fpmix'),
-           ('LiDryer', 'parity'), ('LiDryer', 'serial')]
+           ('LiDryer', 'parity'), ('LiDryer', 'serial'),
+           ('NH3Konnov_edit', 'parity'), ('chempolimi_edit', 'parity')]
 
 COMMON_DEFS = [
     '-D__KINETIX_DEVICE__=', '-D__KINETIX_CONST__=const', "-D__KINETIX_INLINE__=static inline",
