@@ -55,6 +55,11 @@ typedef struct kx_options {
  * (or load from cache) its sm_100a module, make the getters valid. */
 int kx_init(const char* yaml_path, const kx_options* options);
 
+/* Generate + compile the mechanism module into the cache if it is not there yet, WITHOUT touching CUDA
+ * (safe to call before fork(); a multi-process launcher calls it once, like rank 0 running the generator
+ * first in kinetix.cpp:290-296,655-699).  kx_init does this implicitly. */
+int kx_prepare(const char* yaml_path, const kx_options* options);
+
 /* kinetix::isInitialized (kinetix.hpp:15).  Like the reference it becomes true after kx_build. */
 int kx_is_initialized(void);
 

@@ -117,6 +117,41 @@ bool resolve(F& f, const char* sym)
   return f != nullptr;
 }
 
+// Locate the compiled module of (mechanism, options) in the cache, generating + compiling it first if it
+// is missing (cf. kinetix.cpp:655-699: generator through system(), cached by option hash).  No CUDA calls.
+int prepare_module(const char* yaml_path, const kx_options& opt, std::string& lib)
+{
+  const std::string pkg = package_dir();
+  std::string cache = opt.cache_dir ? opt.cache_dir : (getenv("KINETIX_B200_CACHE") ? getenv("KINETIX_B200_CACHE")
+                                                                                     : pkg + "/_cache");
+  std::string tag = stem_of(yaml_path);
+  if (opt.fit_rcp_diff_coeffs) tag += "-rcpdiff";
+  if (opt.single_precision) tag += "-sp";
+  if (opt.block_size > 0) tag += "-b" + std::to_string(opt.block_size);
+  const std::string dir = cache + "/" + tag;
+  lib = dir + "/libkx_mech.so";
+
+  if (!exists(lib) || getenv("KINETIX_B200_REBUILD")) {
+    const char* py = getenv("KINETIX_B200_PYTHON") ? getenv("KINETIX_B200_PYTHON") : "python3";
+    std::string parent = pkg.substr(0, pkg.find_last_of('/'));
+    std::ostringstream cmd;
+    cmd << "PYTHONPATH='" << parent << "':\"$PYTHONPATH\" " << py << " -m kinetix_b200"
+        << " --mechanism '" << yaml_path << "' --output '" << dir << "' --target sm_100a --compile";
+    if (opt.single_precision) cmd << " --single-precision";
+    if (opt.unroll_loops) cmd << " --unroll-loops";
+    if (opt.loop_gibbsexp) cmd << " --loop-gibbsexp";
+    if (opt.group_rxn_unroll) cmd << " --group-rxnunroll";
+    if (opt.group_vis) cmd << " --group-vis";
+    if (opt.nonsym_dij) cmd << " --nonsymDij";
+    if (opt.fit_rcp_diff_coeffs) cmd << " --fit-rcpdiffcoeffs";
+    if (opt.block_size > 0) cmd << " --block-size " << opt.block_size;
+    if (opt.verbose) fprintf(stderr, "[kinetix_b200] %s\n", cmd.str().c_str());
+    if (system(cmd.str().c_str()) != 0 || !exists(lib))
+      return fail("kx_init: error while running the code generator / nvcc: " + cmd.str());
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -151,35 +186,8 @@ int kx_init(const char* yaml_path, const kx_options* opt_in)
   g.device_id = opt.device_id;
   g.single_precision = opt.single_precision != 0;
 
-  // ---- locate / produce the mechanism module (cf. kinetix.cpp:655-699) ----
-  const std::string pkg = package_dir();
-  std::string cache = opt.cache_dir ? opt.cache_dir : (getenv("KINETIX_B200_CACHE") ? getenv("KINETIX_B200_CACHE")
-                                                                                     : pkg + "/_cache");
-  std::string tag = stem_of(yaml_path);
-  if (opt.fit_rcp_diff_coeffs) tag += "-rcpdiff";
-  if (opt.single_precision) tag += "-sp";
-  if (opt.block_size > 0) tag += "-b" + std::to_string(opt.block_size);
-  const std::string dir = cache + "/" + tag;
-  const std::string lib = dir + "/libkx_mech.so";
-
-  if (!exists(lib) || getenv("KINETIX_B200_REBUILD")) {
-    const char* py = getenv("KINETIX_B200_PYTHON") ? getenv("KINETIX_B200_PYTHON") : "python3";
-    std::string parent = pkg.substr(0, pkg.find_last_of('/'));
-    std::ostringstream cmd;
-    cmd << "PYTHONPATH='" << parent << "':\"$PYTHONPATH\" " << py << " -m kinetix_b200"
-        << " --mechanism '" << yaml_path << "' --output '" << dir << "' --target sm_100a --compile";
-    if (opt.single_precision) cmd << " --single-precision";
-    if (opt.unroll_loops) cmd << " --unroll-loops";
-    if (opt.loop_gibbsexp) cmd << " --loop-gibbsexp";
-    if (opt.group_rxn_unroll) cmd << " --group-rxnunroll";
-    if (opt.group_vis) cmd << " --group-vis";
-    if (opt.nonsym_dij) cmd << " --nonsymDij";
-    if (opt.fit_rcp_diff_coeffs) cmd << " --fit-rcpdiffcoeffs";
-    if (opt.block_size > 0) cmd << " --block-size " << opt.block_size;
-    if (opt.verbose) fprintf(stderr, "[kinetix_b200] %s\n", cmd.str().c_str());
-    if (system(cmd.str().c_str()) != 0 || !exists(lib))
-      return fail("kx_init: error while running the code generator / nvcc: " + cmd.str());
-  }
+  std::string lib;
+  if (int e = prepare_module(yaml_path, opt, lib)) return e;
 
   g.module = dlopen(lib.c_str(), RTLD_NOW | RTLD_LOCAL);
   if (!g.module) return fail(std::string("kx_init: dlopen failed: ") + dlerror());
@@ -198,7 +206,7 @@ int kx_init(const char* yaml_path, const kx_options* opt_in)
   }
   if (abi() != 1) {
     unload();
-    return fail("kx_init: module ABI version mismatch, remove the cache directory " + dir);
+    return fail("kx_init: module ABI version mismatch, remove the cached module " + lib);
   }
   // equivalent of the reference's mech.okl query kernels (kinetix.cpp:352-403)
   g.n_species = nsp();
@@ -215,6 +223,17 @@ int kx_init(const char* yaml_path, const kx_options* opt_in)
   }
   g_error.clear();
   return 0;
+}
+
+int kx_prepare(const char* yaml_path, const kx_options* opt_in)
+{
+  if (!yaml_path) return fail("kx_prepare: yaml_path is NULL");
+  kx_options opt;
+  memset(&opt, 0, sizeof(opt));
+  if (opt_in) opt = *opt_in;
+  if (!exists(yaml_path)) return fail(std::string("kx_prepare: mechanism file not found: ") + yaml_path);
+  std::string lib;
+  return prepare_module(yaml_path, opt, lib);
 }
 
 int kx_is_initialized(void) { return g.built ? 1 : 0; }

@@ -67,6 +67,44 @@ def test_bk1_matches_oracle_on_random_states(kinetix, mech):
     assert rate_err <= TOL and hrr_err <= TOL
 
 
+@pytest.mark.parametrize('mech', ['NH3Konnov_edit', 'chempolimi_edit'])
+def test_bk1_plog_mechanisms_across_pressures(kinetix, mech):
+    """pressure-dependent-Arrhenius (P-log) reactions: below, inside and above the tabulated pressures
+    (reference reaction_rates.py:358-388); p != p_ref exercises the non-dimensional pressure argument."""
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech)
+    st = synthetic_states(N, 4000, seed=21)
+    for p in (P_ATM, 1013.25, 5.0e5, 2.0265e6, 2.0e7):
+        new = _run_bk1(kinetix, st, p / P_ATM)
+        ref = orc.production_rates(st, p)
+        rate_err, hrr_err = bk1_errors(new, ref)
+        print(f'{mech} p={p:g} BK1 vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}')
+        assert np.isfinite(new).all() and rate_err <= TOL and hrr_err <= TOL
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    assert max(rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)) <= TOL
+
+
+def test_largest_mechanism_etoh(kinetix):
+    """EtOHKonnov: 129 species / 1231 reactions incl. SRI falloff (BASELINE config 4); oracle = numpy port
+    (the reference's unrolled code needs 5 min of g++ for this mechanism)."""
+    mech = 'EtOHKonnov'
+    N = _setup(kinetix, mech)
+    assert N == 129 and kinetix.nReactions() == 1231
+    orc = Oracle(mech, prefer_ref=False)
+    st = synthetic_states(N, 1500, seed=8)
+    new = _run_bk1(kinetix, st, 1.0)
+    ref = orc.production_rates(st, P_ATM)
+    rate_err, hrr_err = bk1_errors(new, ref)
+    print(f'{mech} BK1 vs port: rates {rate_err:.3e} hrr {hrr_err:.3e}')
+    assert rate_err <= TOL and hrr_err <= TOL
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    errs = rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)
+    print(f'{mech} BK2 vs port: {errs}')
+    assert max(errs) <= TOL
+
+
 @pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
 def test_bk2_matches_oracle_on_random_states(kinetix, mech):
     N = _setup(kinetix, mech)
