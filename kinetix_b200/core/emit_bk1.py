@@ -351,7 +351,7 @@ class BK1Emitter:
                 r = rank[k]
                 pending = max(0, min(ring - 1, len(act_order) - 1 - r))
                 w(f'kx_cp_async_wait<{pending}>();')
-                w(f'const double y{k} = gs[{r % ring} * {block}];')
+                w(f'const double y{k} = kx_ring_read(ring_base + {r % ring} * {block} * 8);')
                 if r + ring < len(act_order):
                     nk = act_order[r + ring]
                     w(f'kx_cp_async8(ring_base + {r % ring} * {block} * 8, sp + {nk} * offset);')

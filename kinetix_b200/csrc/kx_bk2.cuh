@@ -48,6 +48,14 @@ KX_DEVICE double kx_quartic(const double* __restrict__ c, double l)
   return fma(fma(fma(fma(c[4], l, c[3]), l, c[2]), l, c[1]), l, c[0]);
 }
 
+// quartic in ln T of one species pair from 5 coefficients stored as 3 x double2 (shared memory, all lanes
+// read the same address: broadcast).  Estrin form: dependency depth 3 instead of Horner's 4, same 4 DFMA.
+KX_DEVICE double kx_pair_poly(const double2* __restrict__ c, double l, double l2, double l4)
+{
+  const double2 c01 = c[0], c23 = c[1], c4 = c[2];
+  return fma(c4.x, l4, fma(fma(c23.y, l, c23.x), l2, fma(c01.y, l, c01.x)));
+}
+
 // ---- TMA bulk copy + mbarrier plumbing -----------------------------------------------------------
 KX_DEVICE void kx_mbar_init(uint64_t* bar, unsigned count)
 {
@@ -109,6 +117,7 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
   const double T = Tref * kx_ld_stream(state + id);
   const double lnT = kx_log(T);
   const double sqrT = sqrt(T);
+  const double lnT2 = lnT * lnT, lnT4 = lnT2 * lnT2;
 
   // ---- mole fractions (transportProps.okl:23-35) ----
   double rcpMbar = 0.0;
@@ -203,15 +212,18 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
       const double2* __restrict__ tile = reinterpret_cast<const double2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
 #pragma unroll
       for (int i = 0; i < KX_TB; i++) {
+        // one tile row: KX_TB independent (quartic -> reciprocal) chains, then the two accumulations;
+        // the row sum is split in two partial sums to halve its dependency chain
+        double d[KX_TB];
+#pragma unroll
+        for (int j = 0; j < KX_TB; j++) d[j] = kx_rcp(kx_pair_poly(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4));
+        double se = 0.0, so = 0.0;
 #pragma unroll
         for (int j = 0; j < KX_TB; j++) {
-          const double2* c = tile + (i * KX_TB + j) * 3;
-          const double2 c01 = c[0], c23 = c[1], c4 = c[2];
-          const double p = fma(fma(fma(fma(c4.x, lnT, c23.y), lnT, c23.x), lnT, c01.y), lnT, c01.x);
-          const double d = kx_rcp(p);
-          sk[i] = fma(xj[j], d, sk[i]);
-          sj[j] = fma(xk[i], d, sj[j]);
+          if (j & 1) so = fma(xj[j], d[j], so); else se = fma(xj[j], d[j], se);
+          sj[j] = fma(xk[i], d[j], sj[j]);
         }
+        sk[i] += se + so;
       }
 #pragma unroll
       for (int i = 0; i < KX_TB; i++) S[(jb * KX_TB + i) * LD] += sj[i];
@@ -223,15 +235,16 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
       const double2* __restrict__ tile = reinterpret_cast<const double2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
 #pragma unroll
       for (int i = 1; i < KX_TB; i++) {
+        double d[KX_TB];
+#pragma unroll
+        for (int j = 0; j < i; j++) d[j] = kx_rcp(kx_pair_poly(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4));
+        double se = 0.0, so = 0.0;
 #pragma unroll
         for (int j = 0; j < i; j++) {
-          const double2* c = tile + (i * KX_TB + j) * 3;
-          const double2 c01 = c[0], c23 = c[1], c4 = c[2];
-          const double p = fma(fma(fma(fma(c4.x, lnT, c23.y), lnT, c23.x), lnT, c01.y), lnT, c01.x);
-          const double d = kx_rcp(p);
-          sk[i] = fma(xk[j], d, sk[i]);
-          sk[j] = fma(xk[i], d, sk[j]);
+          if (j & 1) so = fma(xk[j], d[j], so); else se = fma(xk[j], d[j], se);
+          sk[j] = fma(xk[i], d[j], sk[j]);
         }
+        sk[i] += se + so;
       }
     }
 #pragma unroll

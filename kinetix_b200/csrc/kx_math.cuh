@@ -138,14 +138,21 @@ KX_DEVICE void kx_st_stream(double* p, double v)
 
 // ---- asynchronous 8-byte global -> shared copy (LDGSTS) with FIFO completion ----------------------
 // One commit group per copy; kx_cp_async_wait<N>() returns when all but the N most recent groups of
-// this thread have landed.
+// this thread have landed; kx_ring_read() must be used to read the landed value.  All three are volatile
+// asm WITHOUT a "memory" clobber: they stay ordered among themselves (which is all the protocol needs)
+// while the compiler remains free to schedule every other memory operation across them.
 KX_DEVICE void kx_cp_async8(unsigned smem_addr, const double* gptr)
 {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n\tcp.async.commit_group;" ::"r"(smem_addr), "l"(gptr)
-               : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n\tcp.async.commit_group;" ::"r"(smem_addr), "l"(gptr));
 }
 template <int N>
 KX_DEVICE void kx_cp_async_wait()
 {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+KX_DEVICE double kx_ring_read(unsigned smem_addr)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_addr));
+  return v;
 }
