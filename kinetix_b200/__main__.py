@@ -37,8 +37,6 @@ def main(argv=None):
     a = p.parse_args(argv)
     if a.target not in ('sm_100a', 'CUDA'):
         sys.exit(f"Error: unsupported --target '{a.target}': kinetix_b200 only emits sm_100a CUDA")
-    if a.single_precision:
-        sys.exit('Error: --single-precision modules are not available in this version')
     transport = str(a.transport).lower() not in ('0', 'false', 'no')
     jit.ensure_module(a.mechanism, a.output, fit_rcp_diff=a.fit_rcpdiffcoeffs,
                       single_precision=a.single_precision, block_size=a.block_size,

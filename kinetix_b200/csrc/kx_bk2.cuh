@@ -43,16 +43,17 @@
 #define KX_CHUNK_MAX (KX_WCHUNK > KX_DCHUNK ? KX_WCHUNK : KX_DCHUNK)
 #define KX_N_DTILES (KX_NB * (KX_NB + 1) / 2)
 
-KX_DEVICE double kx_quartic(const double* __restrict__ c, double l)
+// `real` (double | float) is the arithmetic + table type of the module, `real2` its 2-vector.
+KX_DEVICE real kx_quartic(const real* __restrict__ c, real l)
 {
   return fma(fma(fma(fma(c[4], l, c[3]), l, c[2]), l, c[1]), l, c[0]);
 }
 
 // quartic in ln T of one species pair from 5 coefficients stored as 3 x double2 (shared memory, all lanes
 // read the same address: broadcast).  Estrin form: dependency depth 3 instead of Horner's 4, same 4 DFMA.
-KX_DEVICE double kx_pair_poly(const double2* __restrict__ c, double l, double l2, double l4)
+KX_DEVICE real kx_pair_poly(const real2* __restrict__ c, real l, real l2, real l4)
 {
-  const double2 c01 = c[0], c23 = c[1], c4 = c[2];
+  const real2 c01 = c[0], c23 = c[1], c4 = c[2];
   return fma(c4.x, l4, fma(fma(c23.y, l, c23.x), l2, fma(c01.y, l, c01.x)));
 }
 
@@ -83,24 +84,25 @@ KX_DEVICE void kx_mbar_wait(uint64_t* bar, unsigned parity)
 }
 
 // chunk stream: chunks 0..KX_NB-1 are the Wilke k-blocks, then the KX_N_DTILES diffusion tiles
-KX_DEVICE const double* kx_chunk_src(int c)
+KX_DEVICE const real* kx_chunk_src(int c)
 {
   return c < KX_NB ? kx_wilke + (size_t)c * KX_WCHUNK : kx_diff + (size_t)(c - KX_NB) * KX_DCHUNK;
 }
-KX_DEVICE unsigned kx_chunk_bytes(int c) { return (c < KX_NB ? KX_WCHUNK : KX_DCHUNK) * 8u; }
+KX_DEVICE unsigned kx_chunk_bytes(int c) { return (c < KX_NB ? KX_WCHUNK : KX_DCHUNK) * (unsigned)sizeof(real); }
 
-extern "C" __global__ void __launch_bounds__(KX_BK2_BLOCK, KX_BK2_MINB)
-kx_bk2_f64(const long long n_states, const long long offsetT, const long long offset, const double pressure,
-           const double* __restrict__ state, double* __restrict__ conductivity,
-           double* __restrict__ viscosity, double* __restrict__ rhoD, const double Tref)
+template <typename ST>   // ST: storage type of the state / result buffers (reference: dfloat)
+__global__ void __launch_bounds__(KX_BK2_BLOCK, KX_BK2_MINB)
+kx_bk2(const long long n_states, const long long offsetT, const long long offset, const real pressure,
+       const ST* __restrict__ state, ST* __restrict__ conductivity, ST* __restrict__ viscosity,
+       ST* __restrict__ rhoD, const double Tref)
 {
-  extern __shared__ __align__(16) double kx_sm[];
+  extern __shared__ __align__(16) unsigned char kx_sm_raw[];
   constexpr int LD = KX_BK2_BLOCK;
   constexpr int N_CHUNKS = KX_NB + KX_N_DTILES;
-  double* const buf0 = kx_sm;                                   // 2 x KX_CHUNK_MAX doubles
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(kx_sm + 2 * KX_CHUNK_MAX);   // 2 mbarriers
-  double* __restrict__ X = kx_sm + 2 * KX_CHUNK_MAX + 2 + threadIdx.x;           // X[k] at X[k * LD]
-  double* __restrict__ S = X + KX_NP * LD;                      // b_k = 1/w_k, later the sums S_k
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(kx_sm_raw);                   // 2 mbarriers (16 B)
+  real* const buf0 = reinterpret_cast<real*>(kx_sm_raw + 16);                      // 2 x KX_CHUNK_MAX reals
+  real* __restrict__ X = buf0 + 2 * KX_CHUNK_MAX + threadIdx.x;                    // X[k] at X[k * LD]
+  real* __restrict__ S = X + KX_NP * LD;                        // b_k = 1/w_k, later the sums S_k
 
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = gid < n_states;
@@ -114,39 +116,41 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
     if (N_CHUNKS > 1) kx_bulk_load(buf0 + KX_CHUNK_MAX, kx_chunk_src(1), kx_chunk_bytes(1), &bars[1]);
   }
 
-  const double T = Tref * kx_ld_stream(state + id);
-  const double lnT = kx_log(T);
-  const double sqrT = sqrt(T);
-  const double lnT2 = lnT * lnT, lnT4 = lnT2 * lnT2;
+  const double Td = Tref * (double)kx_ld_stream(state + id);
+  const real T = (real)Td;
+  const real lnT = (real)kx_log(Td);
+  const real sqrT = kx_sqrt(T);
+  const real lnT2 = lnT * lnT, lnT4 = lnT2 * lnT2;
 
   // ---- mole fractions (transportProps.okl:23-35) ----
-  double rcpMbar = 0.0;
+  real rcpMbar = 0;
   {
-    const double* sp = state + id + offsetT;
+    const ST* sp = state + id + offsetT;
 #pragma unroll 8
     for (int k = 0; k < KX_N; k++) {
-      const double w = fmax(0.0, kx_ld_stream(sp + k * offset)) * kx_rcpM[k];
+      const real y = (real)kx_ld_stream(sp + k * offset);
+      const real w = (y > (real)0 ? y : (real)0) * kx_rcpM[k];
       X[k * LD] = w;
       rcpMbar += w;
     }
   }
-  const double Mbar = kx_rcp(rcpMbar);
+  const real Mbar = kx_rcp(rcpMbar);
 
   // ---- conductivity, and per-species viscosity factors ----
   {
-    double s1 = 0.0, s2 = 0.0;
+    real s1 = 0, s2 = 0;
 #pragma unroll 4
     for (int k = 0; k < KX_N; k++) {
-      const double x = X[k * LD] * Mbar;
+      const real x = X[k * LD] * Mbar;
       X[k * LD] = x;
-      const double lam = kx_quartic(kx_cond[k], lnT);
+      const real lam = kx_quartic(kx_cond[k], lnT);
       s1 = fma(x, lam, s1);
       s2 = fma(x, kx_rcp(lam), s2);
-      const double v = kx_quartic(kx_visc[k], lnT);
+      const real v = kx_quartic(kx_visc[k], lnT);
       S[k * LD] = kx_rcp(v * kx_m4[k]);                       // b_k = 1 / w_k
     }
-    for (int k = KX_N; k < KX_NP; k++) { X[k * LD] = 0.0; S[k * LD] = 1.0; }
-    if (live) kx_st_stream(conductivity + id, sqrT * (0.5 * (s1 + kx_rcp(s2))));
+    for (int k = KX_N; k < KX_NP; k++) { X[k * LD] = 0; S[k * LD] = 1; }
+    if (live) kx_st_stream(conductivity + id, (ST)(sqrT * ((real)0.5 * (s1 + kx_rcp(s2)))));
   }
   __syncthreads();   // mbarrier inits visible to all threads before the first wait
 
@@ -164,20 +168,20 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
 
   // ---- viscosity: Wilke with the three-matvec refactoring ----
   {
-    double vis = 0.0;
+    real vis = 0;
     for (int kb = 0; kb < KX_NB; kb++) {
-      double a0[KX_TB], a1[KX_TB], a2[KX_TB];
+      real a0[KX_TB], a1[KX_TB], a2[KX_TB];
 #pragma unroll
-      for (int i = 0; i < KX_TB; i++) a0[i] = a1[i] = a2[i] = 0.0;
+      for (int i = 0; i < KX_TB; i++) a0[i] = a1[i] = a2[i] = 0;
       kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
-      const double* __restrict__ cw = buf0 + (chunk & 1) * KX_CHUNK_MAX;
+      const real* __restrict__ cw = buf0 + (chunk & 1) * KX_CHUNK_MAX;
 #pragma unroll 2
       for (int j = 0; j < KX_N; j++) {
-        const double x = X[j * LD], b = S[j * LD];
-        const double xb = x * b, xbb = xb * b;
+        const real x = X[j * LD], b = S[j * LD];
+        const real xb = x * b, xbb = xb * b;
 #pragma unroll
         for (int i = 0; i < KX_TB; i++) {
-          const double c = cw[j * KX_TB + i];
+          const real c = cw[j * KX_TB + i];
           a0[i] = fma(c, x, a0[i]);
           a1[i] = fma(c, xb, a1[i]);
           a2[i] = fma(c, xbb, a2[i]);
@@ -187,37 +191,37 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
       for (int i = 0; i < KX_TB; i++) {
         const int k = kb * KX_TB + i;
         if (k < KX_N) {
-          const double v = kx_quartic(kx_visc[k], lnT);
-          const double w = v * kx_m4[k];
-          const double phi = fma(w, fma(w, a2[i], a1[i] + a1[i]), a0[i]);
+          const real v = kx_quartic(kx_visc[k], lnT);
+          const real w = v * kx_m4[k];
+          const real phi = fma(w, fma(w, a2[i], a1[i] + a1[i]), a0[i]);
           vis = fma(X[k * LD] * (v * v), kx_rcp(phi), vis);
         }
       }
       advance();
     }
-    if (live) kx_st_stream(viscosity + id, sqrT * vis);
+    if (live) kx_st_stream(viscosity + id, (ST)(sqrT * vis));
   }
 
   // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj, tiles of the lower triangle ----
-  for (int k = 0; k < KX_NP; k++) S[k * LD] = 0.0;
+  for (int k = 0; k < KX_NP; k++) S[k * LD] = 0;
   for (int kb = 0; kb < KX_NB; kb++) {
-    double xk[KX_TB], sk[KX_TB];
+    real xk[KX_TB], sk[KX_TB];
 #pragma unroll
-    for (int i = 0; i < KX_TB; i++) { xk[i] = X[(kb * KX_TB + i) * LD]; sk[i] = 0.0; }
+    for (int i = 0; i < KX_TB; i++) { xk[i] = X[(kb * KX_TB + i) * LD]; sk[i] = 0; }
     for (int jb = 0; jb < kb; jb++) {
-      double xj[KX_TB], sj[KX_TB];
+      real xj[KX_TB], sj[KX_TB];
 #pragma unroll
-      for (int i = 0; i < KX_TB; i++) { xj[i] = X[(jb * KX_TB + i) * LD]; sj[i] = 0.0; }
+      for (int i = 0; i < KX_TB; i++) { xj[i] = X[(jb * KX_TB + i) * LD]; sj[i] = 0; }
       kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
-      const double2* __restrict__ tile = reinterpret_cast<const double2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
+      const real2* __restrict__ tile = reinterpret_cast<const real2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
 #pragma unroll
       for (int i = 0; i < KX_TB; i++) {
         // one tile row: KX_TB independent (quartic -> reciprocal) chains, then the two accumulations;
         // the row sum is split in two partial sums to halve its dependency chain
-        double d[KX_TB];
+        real d[KX_TB];
 #pragma unroll
         for (int j = 0; j < KX_TB; j++) d[j] = kx_rcp(kx_pair_poly(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4));
-        double se = 0.0, so = 0.0;
+        real se = 0, so = 0;
 #pragma unroll
         for (int j = 0; j < KX_TB; j++) {
           if (j & 1) so = fma(xj[j], d[j], so); else se = fma(xj[j], d[j], se);
@@ -232,13 +236,13 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
     // diagonal tile: pairs i > j inside the block
     kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
     {
-      const double2* __restrict__ tile = reinterpret_cast<const double2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
+      const real2* __restrict__ tile = reinterpret_cast<const real2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
 #pragma unroll
       for (int i = 1; i < KX_TB; i++) {
-        double d[KX_TB];
+        real d[KX_TB];
 #pragma unroll
         for (int j = 0; j < i; j++) d[j] = kx_rcp(kx_pair_poly(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4));
-        double se = 0.0, so = 0.0;
+        real se = 0, so = 0;
 #pragma unroll
         for (int j = 0; j < i; j++) {
           if (j & 1) so = fma(xk[j], d[j], so); else se = fma(xk[j], d[j], se);
@@ -254,12 +258,12 @@ kx_bk2_f64(const long long n_states, const long long offsetT, const long long of
 
   // ---- rho * D_km  (mix_transport.py:621-622 and transportProps.okl:43-47; p and Mbar cancel) ----
   if (live) {
-    const double f = sqrT * (1.0 / 8.31446261815324);          // rho*T^1.5/(p*Mbar) = sqrt(T)/R
-    double* out = rhoD + id;
+    const real f = sqrT * (real)(1.0 / 8.31446261815324);      // rho*T^1.5/(p*Mbar) = sqrt(T)/R
+    ST* out = rhoD + id;
 #pragma unroll 4
     for (int k = 0; k < KX_N; k++) {
-      const double num = fma(-kx_M[k], X[k * LD], Mbar);
-      kx_st_stream(out + k * offset, f * num * kx_rcp(S[k * LD]));
+      const real num = fma(-kx_M[k], X[k * LD], Mbar);
+      kx_st_stream(out + k * offset, (ST)(f * num * kx_rcp(S[k * LD])));
     }
   }
   (void)pressure;

@@ -208,6 +208,11 @@ int kx_init(const char* yaml_path, const kx_options* opt_in)
     unload();
     return fail("kx_init: module ABI version mismatch, remove the cached module " + lib);
   }
+  fn_int_t msp = nullptr;
+  if (!resolve(msp, "kxm_single_precision") || (msp() != 0) != g.single_precision) {
+    unload();
+    return fail("kx_init: cached module " + lib + " was generated for a different precision");
+  }
   // equivalent of the reference's mech.okl query kernels (kinetix.cpp:352-403)
   g.n_species = nsp();
   g.n_active = nact();
@@ -252,6 +257,17 @@ int kx_build(double ref_pressure, double ref_temperature, const double* ref_mass
   return 0;
 }
 
+// kernel flavour = f(single_precision at init, storage type), as in the reference (kinetix.cpp:795-799):
+// FP64 module serves FP64 buffers; the --single-precision module serves FP64 buffers ("fpmix") and FP32.
+static int check_dtype(const char* who, int dtype)
+{
+  if (dtype == KX_DTYPE_F64) return 0;
+  if (dtype == KX_DTYPE_F32 && g.single_precision) return 0;
+  return fail(std::string(who) + (dtype == KX_DTYPE_F32
+                                      ? ": FP32 buffers need kx_init with single_precision = 1"
+                                      : ": unknown dtype"));
+}
+
 #define KX_REQUIRE_BUILT(name) \
   if (!g.built) return fail(name ": kx_init/kx_build have not been called")
 
@@ -261,11 +277,10 @@ int kx_production_rates(int64_t n_states, int64_t offsetT, int64_t offset, doubl
   KX_REQUIRE_BUILT("kx_production_rates");
   if (n_states < 0) return fail("kx_production_rates: negative n_states");
   if (n_states && (!d_state || !d_rates)) return fail("kx_production_rates: NULL buffer");
-  if (dtype != KX_DTYPE_F64 || g.single_precision)
-    return fail("kx_production_rates: only FP64 state buffers with FP64 math are built in this version");
+  if (int e = check_dtype("kx_production_rates", dtype)) return e;
   const double pressure_ = pressure * g.ref_pressure;          // kinetix.cpp:802-803
   const double pressure_R = pressure_ / R_GAS;
-  int e = g.rates(n_states, offsetT, offset, pressure_R, pressure_, d_state, d_rates, g.ref_temperature, 0,
+  int e = g.rates(n_states, offsetT, offset, pressure_R, pressure_, d_state, d_rates, g.ref_temperature, dtype,
                   (cudaStream_t)stream);
   return e ? cuda_fail("kx_production_rates", e) : 0;
 }
@@ -278,12 +293,11 @@ int kx_mixture_avg_transport_props(int64_t n_states, int64_t offsetT, int64_t of
   if (n_states < 0) return fail("kx_mixture_avg_transport_props: negative n_states");
   if (n_states && (!d_state || !d_viscosity || !d_conductivity || !d_rho_d))
     return fail("kx_mixture_avg_transport_props: NULL buffer");
-  if (dtype != KX_DTYPE_F64 || g.single_precision)
-    return fail("kx_mixture_avg_transport_props: only FP64 is built in this version");
+  if (int e = check_dtype("kx_mixture_avg_transport_props", dtype)) return e;
   // the reference passes the non-dimensional pressure straight through (kinetix.cpp:832-840); note the
   // kernel argument order conductivity, viscosity
   int e = g.transport(n_states, offsetT, offset, pressure, d_state, d_conductivity, d_viscosity, d_rho_d,
-                      g.ref_temperature, 0, (cudaStream_t)stream);
+                      g.ref_temperature, dtype, (cudaStream_t)stream);
   if (e == 1001) return fail("kx_mixture_avg_transport_props: module was generated without transport");
   return e ? cuda_fail("kx_mixture_avg_transport_props", e) : 0;
 }
@@ -294,10 +308,9 @@ int kx_thermodynamic_props(int64_t n_states, int64_t offsetT, int64_t offset, do
   KX_REQUIRE_BUILT("kx_thermodynamic_props");
   if (n_states < 0) return fail("kx_thermodynamic_props: negative n_states");
   if (n_states && (!d_state || !d_rho || !d_cp_i || !d_rho_cp)) return fail("kx_thermodynamic_props: NULL buffer");
-  if (dtype != KX_DTYPE_F64 || g.single_precision)
-    return fail("kx_thermodynamic_props: only FP64 is built in this version");
+  if (int e = check_dtype("kx_thermodynamic_props", dtype)) return e;
   const double pressure_R = pressure * g.ref_pressure / R_GAS;   // kinetix.cpp:858
-  int e = g.thermo(n_states, offsetT, offset, pressure_R, d_state, d_rho, d_cp_i, d_rho_cp, g.ref_temperature, 0,
+  int e = g.thermo(n_states, offsetT, offset, pressure_R, d_state, d_rho, d_cp_i, d_rho_cp, g.ref_temperature, dtype,
                    (cudaStream_t)stream);
   return e ? cuda_fail("kx_thermodynamic_props", e) : 0;
 }

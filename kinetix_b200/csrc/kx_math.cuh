@@ -136,6 +136,41 @@ KX_DEVICE void kx_st_stream(double* p, double v)
   asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// ---- FP32 flavour (fpmix / fp32 kernels): MUFU approximations, 2^-22 relative ---------------------
+KX_DEVICE float kx_ex2f(float x)
+{
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+KX_DEVICE float kx_lg2f(float x)
+{
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+KX_DEVICE float kx_rcpf(float x)
+{
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// overloads so that templated kernels (csrc/kx_bk2.cuh, kx_thermo.cuh) are written once
+KX_DEVICE float kx_rcp(float a) { return kx_rcpf(a); }
+KX_DEVICE float kx_log(float x) { return kx_lg2f(x) * 0.69314718f; }
+KX_DEVICE float kx_sqrt(float x) { return sqrtf(x); }
+KX_DEVICE double kx_sqrt(double x) { return sqrt(x); }
+KX_DEVICE float kx_ld_stream(const float* p)
+{
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+KX_DEVICE void kx_st_stream(float* p, float v)
+{
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 // ---- asynchronous 8-byte global -> shared copy (LDGSTS) with FIFO completion ----------------------
 // One commit group per copy; kx_cp_async_wait<N>() returns when all but the N most recent groups of
 // this thread have landed; kx_ring_read() must be used to read the landed value.  All three are volatile

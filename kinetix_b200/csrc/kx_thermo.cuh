@@ -5,33 +5,37 @@
 // over the state rows: sum_k w_k and sum_k cp_k/R w_k are accumulated together, so no per-thread array
 // is needed (rhoCp = rho R sum_k (cp_k/R) w_k; the reference's Mbar * rcpMbar factor cancels).
 //
-// The including translation unit defines KX_N and
-//   __constant__ double kx_rcpM[KX_N], kx_Tmid[KX_N], kx_nasa[KX_N][2][7]   (low / high range)
+// The including translation unit defines KX_N, the arithmetic type `real` (double, or float for the
+// --single-precision module) and
+//   __constant__ real kx_rcpM[KX_N], kx_Tmid[KX_N], kx_nasa[KX_N][2][7]   (low / high range)
+// S is the storage type of the state / result buffers (reference: dfloat).
 #pragma once
 #include "kx_math.cuh"
 
-extern "C" __global__ void __launch_bounds__(256)
-kx_thermo_f64(const long long n_states, const long long offsetT, const long long offset, const double pressure_R,
-              const double* __restrict__ state, double* __restrict__ rho, double* __restrict__ cp,
-              double* __restrict__ rhoCp, const double Tref)
+template <typename S>
+__global__ void __launch_bounds__(256)
+kx_thermo(const long long n_states, const long long offsetT, const long long offset, const real pressure_R,
+          const S* __restrict__ state, S* __restrict__ rho, S* __restrict__ cp, S* __restrict__ rhoCp,
+          const double Tref)
 {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_states) return;
-  const double R = 8.31446261815324;
-  const double T = Tref * kx_ld_stream(state + id);
-  const double* sp = state + id + offsetT;
-  double* cpo = cp + id;
-  double rcpMbar = 0.0, cpw = 0.0;
+  const real R = (real)8.31446261815324;
+  const real T = (real)(Tref * (double)kx_ld_stream(state + id));
+  const S* sp = state + id + offsetT;
+  S* cpo = cp + id;
+  real rcpMbar = 0, cpw = 0;
 #pragma unroll 8
   for (int k = 0; k < KX_N; k++) {
-    const double w = fmax(0.0, kx_ld_stream(sp + k * offset)) * kx_rcpM[k];
-    const double* a = kx_nasa[k][T <= kx_Tmid[k] ? 0 : 1];
-    const double cpR = fma(fma(fma(fma(a[4], T, a[3]), T, a[2]), T, a[1]), T, a[0]);
-    kx_st_stream(cpo + k * offset, cpR * R * kx_rcpM[k]);
+    const real y = (real)kx_ld_stream(sp + k * offset);
+    const real w = (y > (real)0 ? y : (real)0) * kx_rcpM[k];
+    const real* a = kx_nasa[k][T <= kx_Tmid[k] ? 0 : 1];
+    const real cpR = fma(fma(fma(fma(a[4], T, a[3]), T, a[2]), T, a[1]), T, a[0]);
+    kx_st_stream(cpo + k * offset, (S)(cpR * R * kx_rcpM[k]));
     rcpMbar += w;
     cpw = fma(cpR, w, cpw);
   }
-  const double rho_ = pressure_R * kx_rcp(T) * kx_rcp(rcpMbar);
-  kx_st_stream(rho + id, rho_);
-  kx_st_stream(rhoCp + id, rho_ * (R * cpw));
+  const real rho_ = pressure_R * kx_rcp(T) * kx_rcp(rcpMbar);
+  kx_st_stream(rho + id, (S)rho_);
+  kx_st_stream(rhoCp + id, (S)(rho_ * (R * cpw)));
 }

@@ -111,7 +111,7 @@ def ensure_module(mechanism_path, output_dir=None, fit_rcp_diff=False, single_pr
     if block_size:
         options.update(block_bk1=int(block_size), block_bk2=int(block_size))
     options.update(emit_options or {})
-    src, stats = emit_module(mech, fits, options)
+    src, stats = emit_module(mech, fits, options, single_precision=single_precision)
     cu = os.path.join(out, 'kx_mech.cu')
     with open(cu, 'w') as fh:
         fh.write(src)

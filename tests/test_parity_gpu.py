@@ -243,6 +243,50 @@ def test_host_buffer_entry_point_matches_device_path(kinetix):
     assert np.array_equal(hv.numpy(), v) and np.array_equal(hc.numpy(), c) and np.array_equal(hrd.numpy(), rd)
 
 
+@pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
+def test_single_precision_modes(kinetix, mech):
+    """--single-precision: FP32 math with FP64 buffers ("fpmix", what the reference CLI runs) and with FP32
+    buffers.  Stated bound: per-state scaled error <= 1e-4 (BK1 rates), 1e-3 (heat release), 5e-5 (BK2), 1e-5
+    (thermo) against the FP64 oracle over the full T in [300, 2500] K range -- the reference's FP32 code is
+    NaN/Inf below ~615 K and its own tolerance is 2e-2 (bk.cpp:198)."""
+    kinetix.init(mech_path(mech), single_precision=True)
+    N = kinetix.nSpecies()
+    kinetix.build(P_ATM, 1.0, [1.0 / N] * N, True)
+    orc = Oracle(mech)
+    st = synthetic_states(N, 20000, seed=31)
+    S = st.shape[1]
+    ref = orc.production_rates(st, P_ATM)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    rho_r, cp_r, rcp_r = orc.thermo(st, P_ATM)
+    for dtype, tdt in ((0, torch.float64), (1, torch.float32)):
+        d_state = torch.from_numpy(st).to(tdt).cuda()
+        d_rates = torch.full_like(d_state, float('nan'))
+        kinetix.productionRates(S, S, S, 1.0, d_state, d_rates, dtype=dtype)
+        visc = torch.empty(S, dtype=tdt, device='cuda')
+        cond = torch.empty_like(visc)
+        rhoD = torch.empty((N, S), dtype=tdt, device='cuda')
+        kinetix.mixtureAvgTransportProps(S, S, S, 1.0, d_state, visc, cond, rhoD, dtype=dtype)
+        rho = torch.empty(S, dtype=tdt, device='cuda')
+        cp = torch.empty((N, S), dtype=tdt, device='cuda')
+        rcp = torch.empty(S, dtype=tdt, device='cuda')
+        kinetix.thermodynamicProps(S, S, S, 1.0, d_state, rho, cp, rcp, dtype=dtype)
+        torch.cuda.synchronize()
+        new = d_rates.double().cpu().numpy()
+        assert np.isfinite(new).all(), 'FP32 path must stay finite down to 300 K'
+        rate_err, hrr_err = bk1_errors(new, ref)
+        e2 = max(rel_err(cond.double().cpu().numpy(), rc), rel_err(visc.double().cpu().numpy(), rv),
+                 rel_err(rhoD.double().cpu().numpy(), rrd))
+        e3 = max(rel_err(rho.double().cpu().numpy(), rho_r), rel_err(cp.double().cpu().numpy(), cp_r),
+                 rel_err(rcp.double().cpu().numpy(), rcp_r))
+        print(f'{mech} single precision dtype={dtype}: BK1 {rate_err:.2e} hrr {hrr_err:.2e} BK2 {e2:.2e} thermo {e3:.2e}')
+        assert rate_err <= 1e-4 and hrr_err <= 1e-3 and e2 <= 5e-5 and e3 <= 1e-5
+    # FP32 buffers without single_precision are rejected, not silently converted
+    kinetix.init(mech_path(mech))
+    kinetix.build(P_ATM, 1.0, [1.0 / N] * N, True)
+    with pytest.raises(kinetix.KinetixError):
+        kinetix.productionRates(S, S, S, 1.0, d_state, d_rates, dtype=1)
+
+
 def test_errors_are_loud(kinetix):
     kinetix.finalize()
     with pytest.raises(kinetix.KinetixError):
