@@ -66,7 +66,7 @@ def test_emitter_produces_a_module(name):
     the kxm_* host interface are present, P-log / SRI reactions are handled."""
     m = mech(name)
     src, stats = emit_module(m, None)
-    for sym in ('kx_bk1_f64', 'kx_thermo_f64', 'kxm_production_rates', 'kxm_transport', 'kxm_thermo',
+    for sym in ('kx_bk1_f64', 'kx_thermo', 'kxm_production_rates', 'kxm_transport', 'kxm_thermo',
                 'kxm_n_species', 'kxm_species_names', 'kxm_molar_masses', 'kxm_abi_version'):
         assert sym in src
     for i in range(m.n_reactions):
@@ -76,6 +76,11 @@ def test_emitter_produces_a_module(name):
         assert 'lnP' in src and 'P >' in src
     if any(r.kind == 'SRI' for r in m.reactions):
         assert 'kx_pow' in src
+    # the --single-precision flavour of the same mechanism: FP32 kernel template + both storage types
+    src32, _ = emit_module(m, None, single_precision=True)
+    assert 'kx_bk1_f32' in src32 and 'typedef float real;' in src32 and 'launch_bk1<float>' in src32
+    for i in range(m.n_reactions):
+        assert f'  // {i + 1}: ' in src32
 
 
 def test_tile_choice():
