@@ -32,9 +32,12 @@ EXP_SAFE = 690.0
 class ConstPool:
     """De-duplicated pool of double constants -> `kc[i]` references."""
 
-    def __init__(self, name='kc', inline=False):
+    PARAM_LIMIT = 3800              # doubles that fit the 32 KB kernel-parameter space beside the other args
+
+    def __init__(self, name='kc', inline=False, as_param=False):
         self.name = name
         self.inline = inline        # emit literals (compiler materialises them) instead of pool loads
+        self.as_param = as_param    # pass the pool BY VALUE as a __grid_constant__ kernel parameter (bank 0)
         self.values = []
         self._index = {}
 
@@ -46,12 +49,25 @@ class ConstPool:
         if key not in self._index:
             self._index[key] = len(self.values)
             self.values.append(v)
-        return f'{self.name}[{self._index[key]}]'
+        i = self._index[key]
+        if self.as_param:
+            # the first PARAM_LIMIT constants travel in the parameter struct, the rest stay __constant__
+            return f'kp.v[{i}]' if i < self.PARAM_LIMIT else f'{self.name}[{i - self.PARAM_LIMIT}]'
+        return f'{self.name}[{i}]'
 
     def definition(self, ctype='double'):
-        vals = self.values or [0.0]
-        body = ',\n  '.join(', '.join(_lit(v) for v in vals[i:i + 4]) for i in range(0, len(vals), 4))
-        return f'__constant__ {ctype} {self.name}[{len(vals)}] = {{\n  {body}\n}};\n'
+        def fmt(vals):
+            vals = vals or [0.0]
+            return ',\n  '.join(', '.join(_lit(v) for v in vals[i:i + 4]) for i in range(0, len(vals), 4)), len(vals)
+        if not self.as_param:
+            body, n = fmt(self.values)
+            return f'__constant__ {ctype} {self.name}[{n}] = {{\n  {body}\n}};\n'
+        head, tail = self.values[:self.PARAM_LIMIT], self.values[self.PARAM_LIMIT:]
+        hb, hn = fmt(head)
+        tb, tn = fmt(tail)
+        return (f'struct KxParamPool {{ {ctype} v[{hn}]; }};\n'
+                f'static const KxParamPool kx_param_pool = {{{{\n  {hb}\n}}}};\n'
+                f'__constant__ {ctype} {self.name}[{tn}] = {{\n  {tb}\n}};\n')
 
 
 def _lit(v):
@@ -216,7 +232,7 @@ class BK1Emitter:
 
     # ---- main --------------------------------------------------------------------------------
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
-             reorder=True, prefetch=4, ring=0, pin_loads=False):
+             reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0):
         """block / min_blocks: launch bounds.
         sync_every: a CTA-wide barrier every that many reactions keeps the warps of a CTA inside the same
           window of the straight-line code so instruction-cache fills are shared (0 = none).
@@ -230,6 +246,13 @@ class BK1Emitter:
           scoreboard shared with younger prefetches."""
         m, N, K = self.m, self.N, self.K
         self.block, self.sync_every, self.gibbs_in_smem = block, sync_every, gibbs_in_smem
+        # keep_until: species whose first reaction comes at or before this schedule position keep their pass-1
+        # value Y_k/M_k in a register until activation (no second read of the state row); early in the
+        # schedule few species are live, so this does not raise the peak register demand
+        self.keep_until = keep_until
+        # l1_keep: pass-1 loads of the state rows allocate in L1 (evict_last) so the reload at activation can hit
+        self.ld1 = 'kx_ld_keep' if l1_keep else 'kx_ld_stream'
+        self.ld2 = 'kx_ld_keep' if l1_keep else 'kx_ld_stream'
         self._flags = {}
         body = []
         self.lines = body
@@ -269,10 +292,14 @@ class BK1Emitter:
         w('double rcpMbar = 0.0;')
         for name in eff_names.values():
             w(f'double {name} = 0.0;')
+        kept = set(k for k in first if first[k] <= keep_until) if keep_until else set()
+        self.kept = kept
+        if kept:
+            w('double ' + ', '.join(f'w{k}' for k in sorted(kept)) + ';')
         w('{')
         for k in range(N):
-            w(f'  const double w{k} = fmax(0.0, kx_ld_stream(sp + {k} * offset)) * {K(1. / m.species[k].M)}; '
-              f'rcpMbar += w{k};')
+            w(f'  {"" if k in kept else "const double "}w{k} = fmax(0.0, {self.ld1}(sp + {k} * offset)) * '
+              f'{K(1. / m.species[k].M)}; rcpMbar += w{k};')
             for vec, name in eff_names.items():
                 if vec[k] != 1:
                     w(f'  {name} = fma({K(vec[k] - 1)}, w{k}, {name});')
@@ -347,7 +374,9 @@ class BK1Emitter:
 
         def activate(k):
             """species k becomes live: concentration, zeroed accumulator, exp(+-g_k/RT)"""
-            if ring:
+            if k in self.kept:
+                w(f'cs{k} = w{k} * rho; wd{k} = 0.0;')
+            elif ring:
                 r = rank[k]
                 pending = max(0, min(ring - 1, len(act_order) - 1 - r))
                 w(f'kx_cp_async_wait<{pending}>();')
@@ -355,7 +384,9 @@ class BK1Emitter:
                 if r + ring < len(act_order):
                     nk = act_order[r + ring]
                     w(f'kx_cp_async8(ring_base + {r % ring} * {block} * 8, sp + {nk} * offset);')
-            if not ring and pin_loads:
+            if k in self.kept:
+                pass
+            elif not ring and pin_loads:
                 # volatile max: keeps this activation ordered after the loads issued `prefetch` activations
                 # ahead (volatile asms are not reordered among themselves), so the compiler cannot sink those
                 # loads down to their first use
@@ -426,9 +457,9 @@ class BK1Emitter:
             if ring:
                 return
             for k in act_order[:upto_rank + 1]:
-                if k not in loaded:
+                if k not in loaded and k not in self.kept:
                     loaded.add(k)
-                    w(f'y{k} = kx_ld_stream(sp + {k} * offset);')
+                    w(f'y{k} = {self.ld2}(sp + {k} * offset);')
 
         emitted = 0
         peak_live, live_now = 0, 0
@@ -550,7 +581,8 @@ class BK1Emitter:
             f'extern "C" __global__ void __launch_bounds__({block}, {min_blocks})',
             f'{kernel_name}(const long long n_states, const long long offsetT, const long long offset,',
             '           const double pressure_R, const double P, const double lnP,',
-            '           const double* __restrict__ state, double* __restrict__ rates, const double Tref)',
+            '           const double* __restrict__ state, double* __restrict__ rates, const double Tref' +
+            (', const __grid_constant__ KxParamPool kp)' if getattr(K, 'as_param', False) else ')'),
             '{',
             '  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;',
             '  const bool live = gid < n_states;',

@@ -72,6 +72,20 @@ KX_DEVICE double kx_exp_nc(double x)
   kd -= MAGIC;
   double r = fma(kd, -6.93147180369123816490e-01, x);
   r = fma(kd, -1.90821492927058770002e-10, r);
+#ifndef KX_EXP_HORNER
+  {
+    // Estrin evaluation of the same degree-11 polynomial: 3 more multiplies, dependency depth 5 instead of 11
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a01 = fma(1.0, r, 1.0), a23 = fma(0.1666666666666668, r, 0.5000000000000019);
+    const double a45 = fma(0.008333333333319601, r, 0.0416666666664881);
+    const double a67 = fma(0.00019841269890047113, r, 0.0013888888952314775);
+    const double a89 = fma(2.755724091857897e-06, r, 2.4801485482328494e-05);
+    const double aab = fma(2.5110037605963777e-08, r, 2.763263963904103e-07);
+    const double b0 = fma(a23, r2, a01), b1 = fma(a67, r2, a45), b2 = fma(aab, r2, a89);
+    const double q = fma(b2, r8, fma(b1, r4, b0));
+    return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
+  }
+#endif
   double p = 2.5110037605963777e-08;
   p = fma(p, r, 2.763263963904103e-07);
   p = fma(p, r, 2.755724091857897e-06);
@@ -129,6 +143,14 @@ KX_DEVICE double kx_ld_stream(const double* p)
 {
   double v;
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+// read-only load that MAY stay in L1: used for the state rows BK1 reads twice (pass 1 for the mean molar
+// mass, then again when a species is activated) so the second read can hit L1 instead of L2.
+KX_DEVICE double kx_ld_keep(const double* p)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 KX_DEVICE void kx_st_stream(double* p, double v)
