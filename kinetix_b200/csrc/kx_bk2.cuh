@@ -57,6 +57,18 @@ KX_DEVICE real kx_pair_poly(const real2* __restrict__ c, real l, real l2, real l
   return fma(c4.x, l4, fma(fma(c23.y, l, c23.x), l2, fma(c01.y, l, c01.x)));
 }
 
+// 1/D_kj from the fitted quartic: a reciprocal, unless the mechanism was generated with
+// --fit-rcpdiffcoeffs, in which case the fit already IS the reciprocal (reference mix_transport.py:198-206,
+// 613-618) and the division disappears.
+KX_DEVICE real kx_pair_rcp_d(const real2* __restrict__ c, real l, real l2, real l4)
+{
+#if KX_RCP_DIFF
+  return kx_pair_poly(c, l, l2, l4);
+#else
+  return kx_rcp(kx_pair_poly(c, l, l2, l4));
+#endif
+}
+
 // ---- TMA bulk copy + mbarrier plumbing -----------------------------------------------------------
 KX_DEVICE void kx_mbar_init(uint64_t* bar, unsigned count)
 {
@@ -220,7 +232,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         // the row sum is split in two partial sums to halve its dependency chain
         real d[KX_TB];
 #pragma unroll
-        for (int j = 0; j < KX_TB; j++) d[j] = kx_rcp(kx_pair_poly(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4));
+        for (int j = 0; j < KX_TB; j++) d[j] = kx_pair_rcp_d(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4);
         real se = 0, so = 0;
 #pragma unroll
         for (int j = 0; j < KX_TB; j++) {
@@ -241,7 +253,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
       for (int i = 1; i < KX_TB; i++) {
         real d[KX_TB];
 #pragma unroll
-        for (int j = 0; j < i; j++) d[j] = kx_rcp(kx_pair_poly(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4));
+        for (int j = 0; j < i; j++) d[j] = kx_pair_rcp_d(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4);
         real se = 0, so = 0;
 #pragma unroll
         for (int j = 0; j < i; j++) {

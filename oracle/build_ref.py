@@ -13,6 +13,7 @@ variants
                                                        (benchmark/src/kinetix.cpp:567-578) -> CPU baseline timing
   fpmix    --single-precision --unroll-loops, -O2    : what `kinetix_bk --single-precision` really runs
                                                        (double storage, float math)
+  rcpdiff  --unroll-loops --fit-rcpdiffcoeffs, -O2   : reciprocal diffusion-coefficient fits (changes BK2 results)
 
 oracle/_ref/ is git-ignored (never committed) but travels to the GPU box.  /root/reference is only
 needed for step 1; if it is absent and the .so already exists the step is skipped.
@@ -31,7 +32,7 @@ OUT = os.path.join(HERE, '_ref')
 
 DEFAULT = [('gri30', 'parity'), ('gri30', 'serial'), ('gri30', 'fpmix'),
            ('LiDryer', 'parity'), ('LiDryer', 'serial'),
-           ('NH3Konnov_edit', 'parity'), ('chempolimi_edit', 'parity')]
+           ('NH3Konnov_edit', 'parity'), ('chempolimi_edit', 'parity'), ('LiDryer', 'rcpdiff')]
 
 COMMON_DEFS = [
     '-D__KINETIX_DEVICE__=', '-D__KINETIX_CONST__=const', "-D__KINETIX_INLINE__=static inline",
@@ -64,6 +65,8 @@ def run_generator(mech, variant):
         cmd.append('--unroll-loops')
     if variant == 'fpmix':
         cmd.append('--single-precision')
+    if variant == 'rcpdiff':
+        cmd += ['--unroll-loops', '--fit-rcpdiffcoeffs']
     env = dict(os.environ, PYTHONPATH=os.path.join(HERE, 'shims'))
     subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL)
 

@@ -30,9 +30,9 @@ def _p(a):
 class Oracle:
     """BK1/BK2/thermo answers for a (N+1, S) state slab: oracle/_ref when built, else the numpy port."""
 
-    def __init__(self, mech, prefer_ref=True):
+    def __init__(self, mech, prefer_ref=True, variant='parity'):
         self.port = oport.Port(mech)
-        self.lib = ref_library(mech) if prefer_ref else None
+        self.lib = ref_library(mech, variant) if prefer_ref else None
         self.kind = 'reference' if self.lib is not None else 'port'
         self.N = self.port.N
 

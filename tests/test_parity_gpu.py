@@ -287,6 +287,28 @@ def test_single_precision_modes(kinetix, mech):
         kinetix.productionRates(S, S, S, 1.0, d_state, d_rates, dtype=1)
 
 
+def test_fit_rcp_diff_coeffs_option(kinetix):
+    """--fit-rcpDiffCoeffs fits 1/D_kj instead of D_kj (no division at run time); results differ from the
+    default at the 1e-4 level, so parity is checked against the reference generated WITH the flag."""
+    mech = 'LiDryer'
+    orc = Oracle(mech, variant='rcpdiff')
+    if orc.kind != 'reference':
+        pytest.skip('oracle/_ref rcpdiff variant not built')
+    kinetix.init(mech_path(mech), fit_rcpDiffCoeffs=True)
+    N = kinetix.nSpecies()
+    kinetix.build(P_ATM, 1.0, [1.0 / N] * N, True)
+    assert '-rcpdiff' in kinetix.modulePath()
+    st = synthetic_states(N, 5000, seed=12)
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    errs = rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)
+    print(f'{mech} BK2 --fit-rcpDiffCoeffs vs reference: {errs}')
+    assert max(errs) <= TOL
+    # and it really is a different fit than the default
+    d_rc, d_rv, d_rrd = Oracle(mech).transport(st, 1.0)
+    assert rel_err(rhoD, d_rrd) > 1e-8
+
+
 def test_errors_are_loud(kinetix):
     kinetix.finalize()
     with pytest.raises(kinetix.KinetixError):
