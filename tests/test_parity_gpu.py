@@ -85,6 +85,23 @@ def test_bk1_plog_mechanisms_across_pressures(kinetix, mech):
     assert max(rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)) <= TOL
 
 
+@pytest.mark.parametrize('mech', ['H2_Konnov', 'H2_new_mech', 'gri30-20', 'gri30-27', 'gri30-35', 'heptaneLu88'])
+def test_remaining_shipped_mechanisms(kinetix, mech):
+    """every mechanism shipped in kinetix/mechanisms goes through the emitter and matches the port
+    (the reference's stock kinetix_bk cannot even run the ones without a Pele directory)."""
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech, prefer_ref=False)
+    st = synthetic_states(N, 3000, seed=17)
+    new = _run_bk1(kinetix, st, 1.0)
+    ref = orc.production_rates(st, P_ATM)
+    rate_err, hrr_err = bk1_errors(new, ref)
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    e2 = max(rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd))
+    print(f'{mech} ({N} sp): BK1 {rate_err:.2e} hrr {hrr_err:.2e} BK2 {e2:.2e}')
+    assert np.isfinite(new).all() and rate_err <= TOL and hrr_err <= TOL and e2 <= TOL
+
+
 def test_largest_mechanism_etoh(kinetix):
     """EtOHKonnov: 129 species / 1231 reactions incl. SRI falloff (BASELINE config 4); oracle = numpy port
     (the reference's unrolled code needs 5 min of g++ for this mechanism)."""
