@@ -337,17 +337,25 @@ def main():
         kinetix.productionRatesHost(Se, Se, Se, 1.0, h_state, h_rates)
         kinetix.mixtureAvgTransportPropsHost(Se, Se, Se, 1.0, h_state, h_visc, h_cond, h_rhoD)
 
+    def e2e_fused_step():
+        kinetix.ratesAndTransportHost(Se, Se, Se, 1.0, h_state, h_rates, h_visc, h_cond, h_rhoD)
+
     e2e_steps = max(3, min(args.steps, 5))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
-    if dist is not None:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = Se * world * e2e_steps / float(e2e_t.item())
+
+    def time_e2e(fn):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return Se * world * e2e_steps / float(t.item())
+
+    e2e_value = time_e2e(e2e_step)
+    e2e_fused = time_e2e(e2e_fused_step)
     h2d = 2 * (N + 1) * Se * 8                      # the state slab is uploaded once per kernel
     d2h = ((N + 1) + (N + 2)) * Se * 8
     assert torch.equal(h_rates[:, :256], rates[:, :256].cpu())
@@ -388,7 +396,9 @@ def main():
         'roofline_other': fp64_roofline('bk1' if dominant == 'bk2' else 'bk2',
                                         bk1_rate if dominant == 'bk2' else bk2_rate),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'states_per_step': Se * world, 'api': 'kx_production_rates_host + kx_mixture_avg_transport_props_host'},
+                'states_per_step': Se * world, 'api': 'kx_production_rates_host + kx_mixture_avg_transport_props_host',
+                'fused_value': e2e_fused, 'fused_api': 'kx_rates_and_transport_host (one state upload)',
+                'fused_h2d_bytes_per_step': (N + 1) * Se * 8},
         'gpu_launches': 2 * args.steps,
         'clocks': clocks,
         'module': os.path.relpath(kinetix.modulePath(), ROOT),

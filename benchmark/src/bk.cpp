@@ -430,7 +430,7 @@ int main(int argc, char** argv)
       printf("avg elapsed time: %.5f s\n", t_bk1);
       printf("avg aggregated throughput: %.2f GRXN/s\n", sps * n_reactions / 1e9);
       printf("avg aggregated throughput: %.4e states/s on %d GPU(s)\n", sps, gpus);
-      if (stem == "gri30")
+      if (stem == "gri30" && !opt.single_precision)
         printf("fraction of FP64 roofline (W = 1.4e4 FP64 instr/state): %.3f\n", sps / gpus * 1.4e4 / FP64_PEAK);
     }
     if (mode == 0 || mode == 2) {
@@ -439,7 +439,7 @@ int main(int argc, char** argv)
       printf("avg elapsed time: %.5f s\n", t_bk2);
       printf("avg aggregated throughput: %.2f GDOF/s\n", sps * (n_species + 2) / 1e9);
       printf("avg aggregated throughput: %.4e states/s on %d GPU(s)\n", sps, gpus);
-      if (stem == "gri30")
+      if (stem == "gri30" && !opt.single_precision)
         printf("fraction of FP64 roofline (W = 2.47e4 FP64 instr/state): %.3f\n", sps / gpus * 2.47e4 / FP64_PEAK);
     }
   }

@@ -94,6 +94,13 @@ int kx_mixture_avg_transport_props_host(int64_t n_states, int64_t offsetT, int64
                                         const double* h_state, double* h_viscosity, double* h_conductivity,
                                         double* h_rho_d);
 
+/* BK1 and BK2 of the same host-resident states with a single upload of the state slab (what one CFD
+ * time step needs).  Not in the reference API: its callers issue productionRates and
+ * mixtureAvgTransportProps back to back on the same o_state (bk.cpp:697-760). */
+int kx_rates_and_transport_host(int64_t n_states, int64_t offsetT, int64_t offset, double pressure,
+                                const double* h_state, double* h_rates, double* h_viscosity,
+                                double* h_conductivity, double* h_rho_d);
+
 /* getters (kinetix.hpp:96-107 / kinetix.cpp:873-908) */
 int kx_n_species(void);
 int kx_n_active_species(void);

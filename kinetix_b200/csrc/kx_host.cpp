@@ -50,10 +50,10 @@ struct State {
   double ref_pressure = 0, ref_temperature = 0, ref_mean_molar_mass = 0;
   std::vector<double> ref_mass_fractions;
   // staging for the host-buffer entry points
-  static const int SLOTS = 2;
-  cudaStream_t streams[SLOTS] = {nullptr, nullptr};
-  void* d_in[SLOTS] = {nullptr, nullptr};
-  void* d_out[SLOTS] = {nullptr, nullptr};
+  static const int SLOTS = 3;
+  cudaStream_t streams[SLOTS] = {nullptr, nullptr, nullptr};
+  void* d_in[SLOTS] = {nullptr, nullptr, nullptr};
+  void* d_out[SLOTS] = {nullptr, nullptr, nullptr};
   size_t in_bytes = 0, out_bytes = 0;
 } g;
 
@@ -318,7 +318,7 @@ int kx_thermodynamic_props(int64_t n_states, int64_t offsetT, int64_t offset, do
 // ---- host-buffer entry points ---------------------------------------------------------------------
 namespace {
 
-const int64_t CHUNK = 1 << 20;   // states per pipelined chunk
+const int64_t CHUNK = 1 << 19;   // states per pipelined chunk (3 slots in flight: H2D | kernels | D2H)
 
 int ensure_staging(size_t in_bytes, size_t out_bytes)
 {
@@ -371,7 +371,7 @@ int kx_production_rates_host(int64_t n_states, int64_t offsetT, int64_t offset, 
   const size_t slab = (size_t)(N + 1) * chunk * sizeof(double);
   if (int e = ensure_staging(slab, slab)) return e;
   int slot = 0;
-  for (int64_t s0 = 0; s0 < n_states; s0 += chunk, slot ^= 1) {
+  for (int64_t s0 = 0; s0 < n_states; s0 += chunk, slot = (slot + 1) % State::SLOTS) {
     const int64_t len = std::min<int64_t>(chunk, n_states - s0);
     cudaStream_t st = g.streams[slot];
     double* din = (double*)g.d_in[slot];
@@ -405,7 +405,7 @@ int kx_mixture_avg_transport_props_host(int64_t n_states, int64_t offsetT, int64
   if (int e = ensure_staging((size_t)(N + 1) * chunk * sizeof(double), (size_t)(N + 2) * chunk * sizeof(double)))
     return e;
   int slot = 0;
-  for (int64_t s0 = 0; s0 < n_states; s0 += chunk, slot ^= 1) {
+  for (int64_t s0 = 0; s0 < n_states; s0 += chunk, slot = (slot + 1) % State::SLOTS) {
     const int64_t len = std::min<int64_t>(chunk, n_states - s0);
     cudaStream_t st = g.streams[slot];
     double* din = (double*)g.d_in[slot];
@@ -426,6 +426,53 @@ int kx_mixture_avg_transport_props_host(int64_t n_states, int64_t offsetT, int64
   for (int s = 0; s < State::SLOTS; s++) {
     cudaError_t e = cudaStreamSynchronize(g.streams[s]);
     if (e != cudaSuccess) return cuda_fail("kx_mixture_avg_transport_props_host: sync", e);
+  }
+  return 0;
+}
+
+// BK1 + BK2 for the same host-resident states with ONE upload of the state slab: what a
+// CFD time step needs (rates and transport coefficients of the same field).
+int kx_rates_and_transport_host(int64_t n_states, int64_t offsetT, int64_t offset, double pressure,
+                                const double* h_state, double* h_rates, double* h_viscosity,
+                                double* h_conductivity, double* h_rho_d)
+{
+  KX_REQUIRE_BUILT("kx_rates_and_transport_host");
+  if (n_states <= 0) return n_states == 0 ? 0 : fail("kx_rates_and_transport_host: negative n_states");
+  if (!h_state || !h_rates || !h_viscosity || !h_conductivity || !h_rho_d)
+    return fail("kx_rates_and_transport_host: NULL buffer");
+  const int N = g.n_species;
+  const int64_t chunk = std::min<int64_t>(CHUNK, n_states);
+  if (int e = ensure_staging((size_t)(N + 1) * chunk * sizeof(double), (size_t)(2 * N + 3) * chunk * sizeof(double)))
+    return e;
+  int slot = 0;
+  for (int64_t s0 = 0; s0 < n_states; s0 += chunk, slot = (slot + 1) % State::SLOTS) {
+    const int64_t len = std::min<int64_t>(chunk, n_states - s0);
+    cudaStream_t st = g.streams[slot];
+    double* din = (double*)g.d_in[slot];
+    double* drates = (double*)g.d_out[slot];                 // (N+1) x len
+    double* dtr = drates + (size_t)(N + 1) * len;            // [viscosity | conductivity | rhoD rows]
+    cudaError_t e = upload_chunk(h_state, s0, len, offsetT, offset, din, st);
+    if (e != cudaSuccess) return cuda_fail("kx_rates_and_transport_host: H2D", e);
+    if (int r = kx_production_rates(len, len, len, pressure, din, drates, KX_DTYPE_F64, st)) return r;
+    if (int r = kx_mixture_avg_transport_props(len, len, len, pressure, din, dtr, dtr + len, dtr + 2 * len,
+                                               KX_DTYPE_F64, st))
+      return r;
+    e = cudaMemcpyAsync(h_rates + s0, drates, len * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(h_rates + s0 + offsetT, offset * sizeof(double), drates + len, len * sizeof(double),
+                            len * sizeof(double), N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(h_viscosity + s0, dtr, len * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(h_conductivity + s0, dtr + len, len * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(h_rho_d + s0, offset * sizeof(double), dtr + 2 * len, len * sizeof(double),
+                            len * sizeof(double), N, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail("kx_rates_and_transport_host: D2H", e);
+  }
+  for (int s = 0; s < State::SLOTS; s++) {
+    cudaError_t e = cudaStreamSynchronize(g.streams[s]);
+    if (e != cudaSuccess) return cuda_fail("kx_rates_and_transport_host: sync", e);
   }
   return 0;
 }

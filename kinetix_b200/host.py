@@ -55,6 +55,7 @@ def library():
     lib.kx_thermodynamic_props.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _int, _vp]
     lib.kx_production_rates_host.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp]
     lib.kx_mixture_avg_transport_props_host.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp, _vp, _vp]
+    lib.kx_rates_and_transport_host.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _vp]
     lib.kx_species_name.argtypes = [_int]
     lib.kx_species_name.restype = ctypes.c_char_p
     lib.kx_species_index.argtypes = [ctypes.c_char_p]
@@ -156,6 +157,13 @@ def mixtureAvgTransportPropsHost(nStates, offsetT, offset, pressure, h_state, h_
     _check(library().kx_mixture_avg_transport_props_host(nStates, offsetT, offset, pressure, _ptr(h_state),
                                                          _ptr(h_viscosity), _ptr(h_conductivity), _ptr(h_rhoD)),
            'kinetix.mixtureAvgTransportPropsHost')
+
+
+def ratesAndTransportHost(n_states, offsetT, offset, pressure, h_state, h_rates, h_viscosity, h_conductivity, h_rhoD):
+    """productionRates + mixtureAvgTransportProps on host buffers with one upload of the state slab."""
+    _check(library().kx_rates_and_transport_host(n_states, offsetT, offset, pressure, _ptr(h_state), _ptr(h_rates),
+                                                 _ptr(h_viscosity), _ptr(h_conductivity), _ptr(h_rhoD)),
+           'kinetix.ratesAndTransportHost')
 
 
 def nSpecies():

@@ -245,7 +245,7 @@ def test_negative_mass_fractions_are_clamped(kinetix):
 def test_host_buffer_entry_point_matches_device_path(kinetix):
     mech = 'gri30'
     N = _setup(kinetix, mech)
-    S = 3000
+    S = 1200000          # > 2 pipeline chunks, ragged tail
     st = synthetic_states(N, S, seed=77)
     dev = _run_bk1(kinetix, st, 1.0)
     h_state = torch.from_numpy(st).pin_memory()
@@ -258,6 +258,12 @@ def test_host_buffer_entry_point_matches_device_path(kinetix):
     hrd = torch.empty((N, S), dtype=torch.float64).pin_memory()
     kinetix.mixtureAvgTransportPropsHost(S, S, S, 1.0, h_state, hv, hc, hrd)
     assert np.array_equal(hv.numpy(), v) and np.array_equal(hc.numpy(), c) and np.array_equal(hrd.numpy(), rd)
+    # fused call: one upload, both kernels
+    for t in (h_rates, hv, hc, hrd):
+        t.fill_(float('nan'))
+    kinetix.ratesAndTransportHost(S, S, S, 1.0, h_state, h_rates, hv, hc, hrd)
+    assert np.array_equal(h_rates.numpy(), dev) and np.array_equal(hv.numpy(), v)
+    assert np.array_equal(hc.numpy(), c) and np.array_equal(hrd.numpy(), rd)
 
 
 @pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
