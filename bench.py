@@ -196,7 +196,7 @@ def cpu_baseline(mech, budget_s=12.0):
     return {'value': n / dt, 'unit': UNIT, 'cores': ref.cores, 'kind': ref.kind, 'sample': ref.describe(passes)}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out=sys.stdout):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
@@ -221,7 +221,7 @@ def run_reference_arm(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     return 0
 
 
@@ -236,7 +236,17 @@ def workload_config(args, per_step_states=None):
 
 
 # ---------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """Only the final JSON line may reach stdout (libraries such as NCCL print banners there): keep the real
+    stdout aside and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -250,7 +260,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
     if args.impl == 'reference':
-        return run_reference_arm(args)
+        return run_reference_arm(args, real_stdout)
 
     import torch
     import kinetix_b200.host as kinetix
@@ -408,7 +418,7 @@ def main():
             line['cpu_baseline'] = cpu_baseline(args.mechanism)
         except Exception as e:     # the baseline is reported, never required for the product number
             line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'unavailable', 'sample': str(e)}
-    print(json.dumps(line))
+    print(json.dumps(line), file=real_stdout, flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
