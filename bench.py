@@ -384,11 +384,20 @@ def main():
     dom_rate, dom_t = (bk2_rate, t_bk2) if dominant == 'bk2' else (bk1_rate, t_bk1)
     alg_bytes = {'bk1': 2 * (N + 1) * 8, 'bk2': (2 * N + 3) * 8}
 
+    traffic_tab = read_json(os.path.join(ROOT, 'profiles', 'traffic_r01.json')) or {}
+
+    def traffic(kernel):
+        """DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch's state count"""
+        t = traffic_tab.get({'bk1': 'kx_bk1_f64', 'bk2': 'kx_bk2'}[kernel]) if args.mechanism == 'gri30' else None
+        if not t:
+            return None
+        return (t['dram_read_bytes'] + t['dram_write_bytes']) / t['states'] * S
+
     def fp64_roofline(kernel, rate):
         ach = rate * W[kernel] * 2 / 1e12        # FP64 TFLOP/s counting one lane instruction as 2 flop (DFMA)
         pk = peak * 2 / 1e12
         return {'bound': 'fp64', 'kernel': f'kx_{kernel}_f64', 'achieved': ach, 'peak': pk, 'unit': 'TFLOP/s',
-                'frac': ach / pk, 'traffic': None, 'fp64_lane_instr_per_state': W[kernel],
+                'frac': ach / pk, 'traffic': traffic(kernel), 'fp64_lane_instr_per_state': W[kernel],
                 'states_per_s': rate, 'roofline_states_per_s': peak / W[kernel], 'peak_source': peak_src,
                 'hbm': {'achieved': rate * alg_bytes[kernel] / 1e9, 'peak': hbm, 'unit': 'GB/s',
                         'frac': rate * alg_bytes[kernel] / 1e9 / hbm, 'bytes_per_state': alg_bytes[kernel],
