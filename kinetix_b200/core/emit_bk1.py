@@ -232,13 +232,18 @@ class BK1Emitter:
 
     # ---- main --------------------------------------------------------------------------------
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
-             reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0):
+             reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True):
         """block / min_blocks: launch bounds.
         sync_every: a CTA-wide barrier every that many reactions keeps the warps of a CTA inside the same
           window of the straight-line code so instruction-cache fills are shared (0 = none).
         gibbs_in_smem: exp(+-g_k) of live species in shared memory slots [slot][thread] (slots are recycled
           when a species retires) instead of registers.
         reorder: liveness-minimising reaction order (see _schedule).
+        live_cap: > 0 limits the number of simultaneously live species (large mechanisms): when a unit would
+          exceed it, the live species whose next use is farthest away is suspended after its latest use -- its
+          partial M_k*wdot_k is written (first time) or added (later) to its own rate row, its heat release
+          added, its shared-memory slots recycled -- and re-activated from the state row at its next use.
+          This is live-range splitting with the (thread-private, L2-resident) output row as the spill slot.
         prefetch: (ring == 0) the state row of a species is re-loaded this many ACTIVATIONS before its own.
         ring: > 0: state rows are re-fetched with cp.async (LDGSTS) into a ring of that many shared-memory
           slots per thread, one commit group per species in activation order; an activation waits with
@@ -262,11 +267,44 @@ class BK1Emitter:
         usp = [self._species_of_unit(u) for u in units]
         order = self._schedule(units, usp, reorder)
         first, last = {}, {}
+        uses = {}
         for pos, ui in enumerate(order):
             for k in usp[ui]:
                 first.setdefault(k, pos)
                 last[k] = pos
+                uses.setdefault(k, []).append(pos)
         self.schedule_stats = dict(units=len(units))
+        # live segments per species: [(start_pos, end_pos)], one segment unless live_cap forces suspensions
+        segments = {k: [[first[k], last[k]]] for k in first}
+        if live_cap:
+            import bisect
+            live_set, seg_start, last_use = set(), {}, {}
+            segments = {k: [] for k in first}
+            for pos, ui in enumerate(order):
+                need = usp[ui]
+                for k in need:
+                    if k not in live_set:
+                        live_set.add(k)
+                        seg_start[k] = pos
+                # suspend the species with the farthest next use while over capacity
+                while len(live_set) > live_cap:
+                    cand = [k for k in live_set if k not in need]
+                    if not cand:
+                        break
+
+                    def next_use(k):
+                        i = bisect.bisect_right(uses[k], pos)
+                        return uses[k][i] if i < len(uses[k]) else 10 ** 9
+                    victim = max(cand, key=next_use)
+                    live_set.discard(victim)
+                    segments[victim].append([seg_start[victim], last_use[victim]])
+                for k in need:
+                    last_use[k] = pos
+                    if pos == last[k]:
+                        live_set.discard(k)
+                        segments[k].append([seg_start[k], pos])
+            n_susp = sum(len(v) - 1 for v in segments.values())
+            self.schedule_stats['suspensions'] = n_susp
 
         # which exp(+-g_k) are needed
         need_pos = [False] * N   # exp(+g): species is a net product of a reversible reaction
@@ -286,35 +324,59 @@ class BK1Emitter:
         for rx in m.reactions:
             if rx.efficiencies is not None and tuple(rx.efficiencies) not in eff_names:
                 eff_names[tuple(rx.efficiencies)] = f'M{len(eff_names)}'
+        # shared-memory slot allocator ([slot][thread] doubles); the Y ring (if any) takes the first slots
+        self.eg_slot, self.rg_slot = {}, {}
+        free_slots, n_slots = [], (ring if ring else 0)
+
+        def take_slot():
+            nonlocal n_slots
+            if free_slots:
+                return free_slots.pop(0)
+            n_slots += 1
+            return n_slots - 1
+
+        if gibbs_in_smem or ring:
+            w('extern __shared__ double kx_sm[];')
+            w('double* const gs = kx_sm + threadIdx.x;')
+        # third-body sums M_i (and ln M_i) are needed all along the reaction list: in shared memory they do not
+        # occupy 2 registers each for the whole kernel (GRI-3.0: 10 + 5 values, EtOHKonnov: 30 + 15)
+        eff_smem = bool(eff_in_smem and gibbs_in_smem)
+        eff_ref = {}
+        for name in eff_names.values():
+            eff_ref[name] = f'gs[{take_slot()} * {block}]' if eff_smem else name
         w('const double T = Tref * kx_ld_stream(state + id);')
         w('const double rcpT = kx_rcp(T);')
         w('const double lnT = kx_log(T);')
-        w('double rcpMbar = 0.0;')
-        for name in eff_names.values():
-            w(f'double {name} = 0.0;')
+        w('double rho, Cm;')
+        if not eff_smem:
+            for name in eff_names.values():
+                w(f'double {name};')
         kept = set(k for k in first if first[k] <= keep_until) if keep_until else set()
         self.kept = kept
         if kept:
             w('double ' + ', '.join(f'w{k}' for k in sorted(kept)) + ';')
         w('{')
+        w('  double rcpMbar = 0.0;')
+        for name in eff_names.values():
+            w(f'  double a{name} = 0.0;')
         for k in range(N):
-            w(f'  {"" if k in kept else "const double "}w{k} = fmax(0.0, {self.ld1}(sp + {k} * offset)) * '
+            w(f'  {"" if k in kept else "const double "}w{k} = fmax(0.0, kx_ld_row<{k}>(sp, offset)) * '
               f'{K(1. / m.species[k].M)}; rcpMbar += w{k};')
             for vec, name in eff_names.items():
                 if vec[k] != 1:
-                    w(f'  {name} = fma({K(vec[k] - 1)}, w{k}, {name});')
-        w('}')
-        w('const double rho = pressure_R * rcpT * kx_rcp(rcpMbar);')
-        w('const double Cm = rho * rcpMbar;')
+                    w(f'  a{name} = fma({K(vec[k] - 1)}, w{k}, a{name});')
+        w('  rho = pressure_R * rcpT * kx_rcp(rcpMbar);')
+        w('  Cm = rho * rcpMbar;')
         for name in eff_names.values():
-            w(f'{name} = fma(rho, {name}, Cm);')
+            w(f'  {eff_ref[name]} = fma(rho, a{name}, Cm);')
+        w('}')
         w(f'const double C0 = {K(const.ONE_ATM / const.R_GAS)} * rcpT;')
         w(f'const double rcpC0 = {K(const.R_GAS / const.ONE_ATM)} * T;')
         flag_pos = len(body)
 
         def collider(rx):
             if rx.efficiencies is not None:
-                return eff_names[tuple(rx.efficiencies)]
+                return eff_ref[eff_names[tuple(rx.efficiencies)]]
             if rx.third_body_index >= 0:
                 return f'cs{rx.third_body_index}'
             return 'Cm'
@@ -328,8 +390,12 @@ class BK1Emitter:
                 arg, _ = self.ratio_expr(rx)
                 if not name.startswith('cs'):
                     if arg is not None and name not in ln_collider:
-                        v = 'ln_' + name
-                        w(f'const double {v} = kx_log(fmax({name}, 1e-300));')
+                        if eff_smem:
+                            v = f'gs[{take_slot()} * {block}]'
+                            w(f'{v} = kx_log(fmax({name}, 1e-300));')
+                        else:
+                            v = 'ln_' + name
+                            w(f'const double {v} = kx_log(fmax({name}, 1e-300));')
                         self.stats['log'] += 1
                         ln_collider[name] = v
 
@@ -340,15 +406,8 @@ class BK1Emitter:
         if not ring:
             w('double ' + ', '.join(f'y{k}' for k in used) + ';')
         w('double hsum = 0.0;')
-        self.eg_slot, self.rg_slot = {}, {}
-        free_slots, n_slots = [], 0
         act_order = sorted(used, key=lambda k: (first[k], k))      # activation order
         rank = {k: i for i, k in enumerate(act_order)}
-        if ring:
-            n_slots = ring                                          # slots [0, ring) = the Y ring
-        if gibbs_in_smem or ring:
-            w('extern __shared__ double kx_sm[];')
-            w('double* const gs = kx_sm + threadIdx.x;')
         if ring:
             w('const unsigned ring_base = (unsigned)__cvta_generic_to_shared(gs);')
             for k in act_order[:ring]:
@@ -358,13 +417,6 @@ class BK1Emitter:
             if names:
                 w('double ' + ', '.join(names) + ';')
 
-        def take_slot():
-            nonlocal n_slots
-            if free_slots:
-                return free_slots.pop(0)
-            n_slots += 1
-            return n_slots - 1
-
         def gcoef(a):   # g/RT = b0 + b1 lnT + b6/T + T (b2 + T (b3 + T (b4 + T b5)))   (reaction_rates.py:565-569)
             return [a[0] - a[6], -a[0], -a[1] / 2, (1. / 3. - 1. / 2.) * a[2], (1. / 4. - 1. / 3.) * a[3],
                     (1. / 5. - 1. / 4.) * a[4], a[5]]
@@ -372,11 +424,11 @@ class BK1Emitter:
         def hcoef(a):   # h/RT (thermodynamics.py:74-75)
             return [a[0], a[1] / 2, a[2] / 3, a[3] / 4, a[4] / 5, a[5]]
 
-        def activate(k):
+        def activate(k, reactivation=False):
             """species k becomes live: concentration, zeroed accumulator, exp(+-g_k/RT)"""
-            if k in self.kept:
+            if k in self.kept and not reactivation:
                 w(f'cs{k} = w{k} * rho; wd{k} = 0.0;')
-            elif ring:
+            elif ring and not reactivation:
                 r = rank[k]
                 pending = max(0, min(ring - 1, len(act_order) - 1 - r))
                 w(f'kx_cp_async_wait<{pending}>();')
@@ -384,8 +436,10 @@ class BK1Emitter:
                 if r + ring < len(act_order):
                     nk = act_order[r + ring]
                     w(f'kx_cp_async8(ring_base + {r % ring} * {block} * 8, sp + {nk} * offset);')
-            if k in self.kept:
+            if k in self.kept and not reactivation:
                 pass
+            elif reactivation:
+                w(f'cs{k} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); wd{k} = 0.0;')
             elif not ring and pin_loads:
                 # volatile max: keeps this activation ordered after the loads issued `prefetch` activations
                 # ahead (volatile asms are not reordered among themselves), so the compiler cannot sink those
@@ -422,11 +476,14 @@ class BK1Emitter:
                 w(f'  {self.RG(k)} = {self.exp("-g", -ghi, -glo)};')
             w('}')
 
-        def retire(k):
-            """last use of species k is behind us: write its rate row, add its heat release, free its slots
-            (productionRates.okl:48-62)"""
+        def retire(k, first_flush=True):
+            """species k leaves the live set (for good, or suspended under live_cap): write / add its rate row,
+            add its heat release, free its slots (productionRates.okl:48-62)"""
             c, _, _ = self.nasa_select(k, hcoef)
-            w(f'if (live) kx_st_stream(out + {k} * offset, {K(m.species[k].M)} * wd{k});')
+            if first_flush:
+                w(f'if (live) kx_st_row<{k}>(out, offset, {K(m.species[k].M)} * wd{k});')
+            else:
+                w(f'if (live) kx_add_row<{k}>(out, offset, {K(m.species[k].M)} * wd{k});')
             w(f'hsum = fma(wd{k}, fma(fma(fma(fma({c[4]}, T, {c[3]}), T, {c[2]}), T, {c[1]}), T, '
               f'fma({c[5]}, rcpT, {c[0]})), hsum);')
             for slots in (self.eg_slot, self.rg_slot):
@@ -442,15 +499,17 @@ class BK1Emitter:
         # species that never occur in a reaction: rate row is zero (the reference's wdot[k] stays 0)
         for k in range(N):
             if k not in first:
-                w(f'if (live) kx_st_stream(out + {k} * offset, 0.0);')
+                w(f'if (live) kx_st_row<{k}>(out, offset, 0.0);')
 
         # ---- units in schedule order ---------------------------------------------------------------
-        by_first = {}
-        for k, pos in first.items():
-            by_first.setdefault(pos, []).append(k)
-        by_last = {}
-        for k, pos in last.items():
-            by_last.setdefault(pos, []).append(k)
+        by_first, by_last = {}, {}
+        seg_index = {}
+        for k, segs in segments.items():
+            for si, (a, b) in enumerate(segs):
+                by_first.setdefault(a, []).append(k)
+                by_last.setdefault(b, []).append(k)
+                seg_index[(k, a)] = si
+                seg_index[(k, 'end', b)] = si
         loaded = set()
 
         def issue_loads(upto_rank):
@@ -459,15 +518,18 @@ class BK1Emitter:
             for k in act_order[:upto_rank + 1]:
                 if k not in loaded and k not in self.kept:
                     loaded.add(k)
-                    w(f'y{k} = {self.ld2}(sp + {k} * offset);')
+                    w(f'y{k} = kx_ld_row<{k}>(sp, offset);')
 
         emitted = 0
         peak_live, live_now = 0, 0
         for pos, ui in enumerate(order):
             members = units[ui]
             for k in sorted(by_first.get(pos, [])):
-                issue_loads(rank[k] + prefetch)
-                activate(k)
+                if seg_index[(k, pos)] == 0:
+                    issue_loads(rank[k] + prefetch)
+                else:                                   # re-activation after a suspension: fresh load
+                    w(f'y{k} = kx_ld_row<{k}>(sp, offset);')
+                activate(k, reactivation=seg_index[(k, pos)] > 0)
                 live_now += 1
             peak_live = max(peak_live, live_now)
             if sync_every and emitted and emitted // sync_every != (emitted + len(members)) // sync_every:
@@ -566,7 +628,7 @@ class BK1Emitter:
                 w('  }')
             w('}')
             for k in sorted(by_last.get(pos, [])):
-                retire(k)
+                retire(k, first_flush=seg_index[(k, 'end', pos)] == 0)
                 live_now -= 1
         w(f'if (live) kx_st_stream(rates + id, {K(-const.R_GAS)} * T * hsum);')
 

@@ -145,6 +145,33 @@ KX_DEVICE double kx_ld_stream(const double* p)
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+// Row accesses of the species-major slabs: element `base[K * offset]`.  The address arithmetic happens INSIDE
+// the volatile asm: otherwise the compiler computes all 2 x N row addresses up front, cannot keep them in
+// registers and spills them (GRI-3.0: 0.75 KB, EtOHKonnov: 3 KB of local memory per thread were nothing but
+// addresses).  One 64-bit multiply-add per access instead.
+template <int K>
+KX_DEVICE double kx_ld_row(const double* base, long long offset)
+{
+  double v;
+  asm volatile("{\n\t.reg .s64 a;\n\tmad.lo.s64 a, %2, %3, %1;\n\tld.global.nc.L1::no_allocate.f64 %0, [a];\n\t}"
+               : "=d"(v) : "l"(base), "l"(offset), "n"(K * 8));
+  return v;
+}
+template <int K>
+KX_DEVICE void kx_st_row(double* base, long long offset, double v)
+{
+  asm volatile("{\n\t.reg .s64 a;\n\tmad.lo.s64 a, %1, %2, %0;\n\tst.global.L1::no_allocate.f64 [a], %3;\n\t}"
+               ::"l"(base), "l"(offset), "n"(K * 8), "d"(v) : "memory");
+}
+// base[K*offset] += v  (thread-private element: partial rate rows under live_cap)
+template <int K>
+KX_DEVICE void kx_add_row(double* base, long long offset, double v)
+{
+  asm volatile("{\n\t.reg .s64 a;\n\t.reg .f64 t;\n\tmad.lo.s64 a, %1, %2, %0;\n\tld.global.f64 t, [a];\n\t"
+               "add.f64 t, t, %3;\n\tst.global.f64 [a], t;\n\t}"
+               ::"l"(base), "l"(offset), "n"(K * 8), "d"(v) : "memory");
+}
+
 // read-only load that MAY stay in L1: used for the state rows BK1 reads twice (pass 1 for the mean molar
 // mass, then again when a species is activated) so the second read can hit L1 instead of L2.
 KX_DEVICE double kx_ld_keep(const double* p)
