@@ -118,14 +118,37 @@ class BK1Emitter:
     # ---- thermo ------------------------------------------------------------------------------
     def nasa_select(self, k, make):
         """coefficient list for species k selected on T <= T_mid; `make(a)` maps the 7 NASA
-        coefficients to the derived coefficients actually needed."""
+        coefficients to the derived coefficients actually needed.
+        nasa_indexed: the low-range sets of all species live in the first half of one __constant__ table and
+        the high-range sets in the second half; a per-T_mid integer offset (0 or half) picks the range, so a
+        coefficient is ONE constant load with a register offset instead of two loads and a 64-bit select."""
         s = self.m.species[k]
         lo, hi = make(s.nasa_lo), make(s.nasa_hi)
+        if getattr(self, 'nasa_indexed', False):
+            base = len(self.nasa_lo_tab)
+            self.nasa_lo_tab += [float(v) for v in lo]
+            self.nasa_hi_tab += [float(v) for v in hi]
+            off = self.tmid_offset(s.T_mid)
+            return [f'kx_nasa_tab[{off} + {base + i}]' for i in range(len(lo))], lo, hi
         flag = self.tmid_flag(s.T_mid)
         out = []
         for a, b in zip(lo, hi):
             out.append(self.K(a) if a == b else f'({flag} ? {self.K(a)} : {self.K(b)})')
         return out, lo, hi
+
+    def tmid_offset(self, tmid):
+        name = 'noff_' + repr(float(tmid)).replace('.', '_').replace('-', 'm')
+        if name not in self._flags:
+            self._flags[name] = f'const int {name} = (T <= {_lit(float(tmid))}) ? 0 : KX_NASA_HALF;'
+        return name
+
+    def nasa_table_definition(self):
+        if not getattr(self, 'nasa_indexed', False):
+            return ''
+        vals = self.nasa_lo_tab + self.nasa_hi_tab
+        body = ',\n  '.join(', '.join(_lit(v) for v in vals[i:i + 4]) for i in range(0, len(vals), 4))
+        return (f'#define KX_NASA_HALF {len(self.nasa_lo_tab)}\n'
+                f'__constant__ double kx_nasa_tab[{len(vals)}] = {{\n  {body}\n}};\n')
 
     def tmid_flag(self, tmid):
         name = 'lo_' + repr(float(tmid)).replace('.', '_').replace('-', 'm')
@@ -232,7 +255,7 @@ class BK1Emitter:
 
     # ---- main --------------------------------------------------------------------------------
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
-             reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True):
+             reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False):
         """block / min_blocks: launch bounds.
         sync_every: a CTA-wide barrier every that many reactions keeps the warps of a CTA inside the same
           window of the straight-line code so instruction-cache fills are shared (0 = none).
@@ -251,6 +274,7 @@ class BK1Emitter:
           scoreboard shared with younger prefetches."""
         m, N, K = self.m, self.N, self.K
         self.block, self.sync_every, self.gibbs_in_smem = block, sync_every, gibbs_in_smem
+        self.nasa_indexed, self.nasa_lo_tab, self.nasa_hi_tab = nasa_indexed, [], []
         # keep_until: species whose first reaction comes at or before this schedule position keep their pass-1
         # value Y_k/M_k in a register until activation (no second read of the state row); early in the
         # schedule few species are live, so this does not raise the peak register demand
