@@ -64,6 +64,8 @@ KX_DEVICE real kx_pair_rcp_d(const real2* __restrict__ c, real l, real l2, real 
 {
 #if KX_RCP_DIFF
   return kx_pair_poly(c, l, l2, l4);
+#elif defined(KX_BK2_FAST_RCP)
+  return kx_rcp_fast(kx_pair_poly(c, l, l2, l4));
 #else
   return kx_rcp(kx_pair_poly(c, l, l2, l4));
 #endif
@@ -150,15 +152,27 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   const real lnT2 = lnT * lnT, lnT4 = lnT2 * lnT2;
 
   // ---- mole fractions (transportProps.okl:23-35) ----
+  // The state rows are fetched in batches of up to 32 independent loads (one DRAM round trip per batch):
+  // with a single CTA per SM nothing else hides this latency.
   real rcpMbar = 0;
   {
     const ST* sp = state + id + offsetT;
-#pragma unroll 8
-    for (int k = 0; k < KX_N; k++) {
-      const real y = (real)kx_ld_stream(sp + k * offset);
-      const real w = (y > (real)0 ? y : (real)0) * kx_rcpM[k];
-      X[k * LD] = w;
-      rcpMbar += w;
+    constexpr int LB = 32;
+#pragma unroll 1
+    for (int k0 = 0; k0 < KX_N; k0 += LB) {
+      ST y[LB];
+#pragma unroll
+      for (int i = 0; i < LB; i++)
+        if (k0 + i < KX_N) y[i] = kx_ld_stream(sp + (size_t)(k0 + i) * offset);
+#pragma unroll
+      for (int i = 0; i < LB; i++) {
+        if (k0 + i < KX_N) {
+          const real yi = (real)y[i];
+          const real w = (yi > (real)0 ? yi : (real)0) * kx_rcpM[k0 + i];
+          X[(k0 + i) * LD] = w;
+          rcpMbar += w;
+        }
+      }
     }
   }
   const real Mbar = kx_rcp(rcpMbar);
@@ -166,7 +180,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   // ---- conductivity, and per-species viscosity factors ----
   {
     real s1 = 0, s2 = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < KX_N; k++) {
       const real x = X[k * LD] * Mbar;
       X[k * LD] = x;

@@ -30,6 +30,15 @@ KX_DEVICE double kx_rcp(double a)
   return fma(x, e, x);
 }
 
+// Reciprocal with ONE quadratic Newton step: x0 (2 - a x0), 2 FP64 ops, relative error e0^2 ~ 1e-12.
+// Used only where the result feeds sums of positive terms (BK2 pair loop), 100x inside the 1e-10 contract.
+KX_DEVICE double kx_rcp_fast(double a)
+{
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  return x * fma(-a, x, 2.0);
+}
+
 // a / b with the reciprocal above (one extra DMUL); relative error ~2e-16.
 KX_DEVICE double kx_div(double a, double b) { return a * kx_rcp(b); }
 
@@ -241,6 +250,7 @@ KX_DEVICE float kx_rcpf(float x)
 }
 // overloads so that templated kernels (csrc/kx_bk2.cuh, kx_thermo.cuh) are written once
 KX_DEVICE float kx_rcp(float a) { return kx_rcpf(a); }
+KX_DEVICE float kx_rcp_fast(float a) { return kx_rcpf(a); }
 KX_DEVICE float kx_log(float x) { return kx_lg2f(x) * 0.69314718f; }
 KX_DEVICE float kx_sqrt(float x) { return sqrtf(x); }
 KX_DEVICE double kx_sqrt(double x) { return sqrt(x); }
