@@ -40,7 +40,7 @@
 #include "kx_math.cuh"
 
 #define KX_NB (KX_NP / KX_TB)
-#define KX_CHUNK_MAX (KX_WCHUNK > KX_DCHUNK ? KX_WCHUNK : KX_DCHUNK)
+// KX_CHUNK_MAX (reals per streaming buffer) is defined by the including translation unit
 #define KX_N_DTILES (KX_NB * (KX_NB + 1) / 2)
 
 // `real` (double | float) is the arithmetic + table type of the module, `real2` its 2-vector.
@@ -97,12 +97,23 @@ KX_DEVICE void kx_mbar_wait(uint64_t* bar, unsigned parity)
       : "memory");
 }
 
-// chunk stream: chunks 0..KX_NB-1 are the Wilke k-blocks, then the KX_N_DTILES diffusion tiles
+// chunk stream: the KX_NB Wilke k-blocks, then the KX_N_DTILES diffusion tiles.  With KX_SPLIT == 2 every
+// table block is streamed as two sub-chunks (Wilke: columns j < KX_J0 / the rest; tiles: rows i < KX_R0 / the
+// rest) so that the double buffer is half as large and TWO 128-thread CTAs fit one SM's shared memory: one
+// CTA's memory-bound prologue / epilogue then overlaps the other's FP64 phases.
 KX_DEVICE const real* kx_chunk_src(int c)
 {
-  return c < KX_NB ? kx_wilke + (size_t)c * KX_WCHUNK : kx_diff + (size_t)(c - KX_NB) * KX_DCHUNK;
+  const int blk = c / KX_SPLIT, h = c % KX_SPLIT;
+  if (blk < KX_NB) return kx_wilke + (size_t)blk * KX_WCHUNK + (h ? KX_J0 * KX_TB : 0);
+  return kx_diff + (size_t)(blk - KX_NB) * KX_DCHUNK + (h ? KX_R0 * KX_TB * 6 : 0);
 }
-KX_DEVICE unsigned kx_chunk_bytes(int c) { return (c < KX_NB ? KX_WCHUNK : KX_DCHUNK) * (unsigned)sizeof(real); }
+KX_DEVICE unsigned kx_chunk_bytes(int c)
+{
+  const int blk = c / KX_SPLIT, h = c % KX_SPLIT;
+  const int whole = blk < KX_NB ? KX_WCHUNK : KX_DCHUNK;
+  const int first = blk < KX_NB ? KX_J0 * KX_TB : KX_R0 * KX_TB * 6;
+  return (unsigned)(KX_SPLIT == 1 ? whole : (h ? whole - first : first)) * (unsigned)sizeof(real);
+}
 
 template <typename ST>   // ST: storage type of the state / result buffers (reference: dfloat)
 __global__ void __launch_bounds__(KX_BK2_BLOCK, KX_BK2_MINB)
@@ -112,7 +123,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 {
   extern __shared__ __align__(16) unsigned char kx_sm_raw[];
   constexpr int LD = KX_BK2_BLOCK;
-  constexpr int N_CHUNKS = KX_NB + KX_N_DTILES;
+  constexpr int N_CHUNKS = (KX_NB + KX_N_DTILES) * KX_SPLIT;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(kx_sm_raw);                   // 2 mbarriers (16 B)
   real* const buf0 = reinterpret_cast<real*>(kx_sm_raw + 16);                      // 2 x KX_CHUNK_MAX reals
   real* __restrict__ X = buf0 + 2 * KX_CHUNK_MAX + threadIdx.x;                    // X[k] at X[k * LD]
@@ -214,31 +225,37 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
       real a0[KX_TB], a1[KX_TB], a2[KX_TB];
 #pragma unroll
       for (int i = 0; i < KX_TB; i++) a0[i] = a1[i] = a2[i] = 0;
-      kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
-      const real* __restrict__ cw = buf0 + (chunk & 1) * KX_CHUNK_MAX;
+#pragma unroll
+      for (int h = 0; h < KX_SPLIT; h++) {
+        const int j_lo = h ? KX_J0 : 0, j_hi = (KX_SPLIT == 1 || h) ? KX_N : KX_J0;
+        kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
+        const real* __restrict__ cw = buf0 + (chunk & 1) * KX_CHUNK_MAX - j_lo * KX_TB;
 #pragma unroll 2
-      for (int j = 0; j < KX_N; j++) {
-        const real x = X[j * LD], b = KX_S_LOAD(j);
-        const real xb = x * b, xbb = xb * b;
+        for (int j = j_lo; j < j_hi; j++) {
+          const real x = X[j * LD], b = KX_S_LOAD(j);
+          const real xb = x * b, xbb = xb * b;
 #pragma unroll
-        for (int i = 0; i < KX_TB; i++) {
-          const real c = cw[j * KX_TB + i];
-          a0[i] = fma(c, x, a0[i]);
-          a1[i] = fma(c, xb, a1[i]);
-          a2[i] = fma(c, xbb, a2[i]);
+          for (int i = 0; i < KX_TB; i++) {
+            const real c = cw[j * KX_TB + i];
+            a0[i] = fma(c, x, a0[i]);
+            a1[i] = fma(c, xb, a1[i]);
+            a2[i] = fma(c, xbb, a2[i]);
+          }
         }
-      }
+        if (h == KX_SPLIT - 1) {
 #pragma unroll
-      for (int i = 0; i < KX_TB; i++) {
-        const int k = kb * KX_TB + i;
-        if (k < KX_N) {
-          const real v = kx_quartic(kx_visc[k], lnT);
-          const real w = v * kx_m4[k];
-          const real phi = fma(w, fma(w, a2[i], a1[i] + a1[i]), a0[i]);
-          vis = fma(X[k * LD] * (v * v), kx_rcp(phi), vis);
+          for (int i = 0; i < KX_TB; i++) {
+            const int k = kb * KX_TB + i;
+            if (k < KX_N) {
+              const real v = kx_quartic(kx_visc[k], lnT);
+              const real w = v * kx_m4[k];
+              const real phi = fma(w, fma(w, a2[i], a1[i] + a1[i]), a0[i]);
+              vis = fma(X[k * LD] * (v * v), kx_rcp(phi), vis);
+            }
+          }
         }
+        advance();
       }
-      advance();
     }
     if (live) kx_st_stream(viscosity + id, (ST)(sqrT * vis));
   }
@@ -255,33 +272,45 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         xj[i] = X[(jb * KX_TB + i) * LD];
         sj[i] = KX_S_LOAD(jb * KX_TB + i);
       }
-      kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
-      const real2* __restrict__ tile = reinterpret_cast<const real2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
 #pragma unroll
-      for (int i = 0; i < KX_TB; i++) {
-        // one tile row: KX_TB independent (quartic -> reciprocal) chains, then the two accumulations;
-        // the row sum is split in two partial sums to halve its dependency chain
-        real d[KX_TB];
+      for (int h = 0; h < KX_SPLIT; h++) {
+        const int i_lo = h ? KX_R0 : 0, i_hi = (KX_SPLIT == 1 || h) ? KX_TB : KX_R0;
+        kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
+        const real2* __restrict__ tile =
+            reinterpret_cast<const real2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX) - i_lo * KX_TB * 3;
 #pragma unroll
-        for (int j = 0; j < KX_TB; j++) d[j] = kx_pair_rcp_d(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4);
-        real se = 0, so = 0;
+        for (int i = 0; i < KX_TB; i++) {
+          if (i < i_lo || i >= i_hi) continue;
+          // one tile row: KX_TB independent (quartic -> reciprocal) chains, then the two accumulations;
+          // the row sum is split in two partial sums to halve its dependency chain
+          real d[KX_TB];
 #pragma unroll
-        for (int j = 0; j < KX_TB; j++) {
-          if (j & 1) so = fma(xj[j], d[j], so); else se = fma(xj[j], d[j], se);
-          sj[j] = fma(xk[i], d[j], sj[j]);
+          for (int j = 0; j < KX_TB; j++) d[j] = kx_pair_rcp_d(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4);
+          real se = 0, so = 0;
+#pragma unroll
+          for (int j = 0; j < KX_TB; j++) {
+            if (j & 1) so = fma(xj[j], d[j], so); else se = fma(xj[j], d[j], se);
+            sj[j] = fma(xk[i], d[j], sj[j]);
+          }
+          sk[i] += se + so;
         }
-        sk[i] += se + so;
-      }
+        if (h == KX_SPLIT - 1) {
 #pragma unroll
-      for (int i = 0; i < KX_TB; i++) KX_S_STORE(jb * KX_TB + i, sj[i]);
-      advance();
+          for (int i = 0; i < KX_TB; i++) KX_S_STORE(jb * KX_TB + i, sj[i]);
+        }
+        advance();
+      }
     }
     // diagonal tile: pairs i > j inside the block
-    kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
-    {
-      const real2* __restrict__ tile = reinterpret_cast<const real2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX);
+#pragma unroll
+    for (int h = 0; h < KX_SPLIT; h++) {
+      const int i_lo = h ? KX_R0 : 0, i_hi = (KX_SPLIT == 1 || h) ? KX_TB : KX_R0;
+      kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
+      const real2* __restrict__ tile =
+          reinterpret_cast<const real2*>(buf0 + (chunk & 1) * KX_CHUNK_MAX) - i_lo * KX_TB * 3;
 #pragma unroll
       for (int i = 1; i < KX_TB; i++) {
+        if (i < i_lo || i >= i_hi) continue;
         real d[KX_TB];
 #pragma unroll
         for (int j = 0; j < i; j++) d[j] = kx_pair_rcp_d(tile + (i * KX_TB + j) * 3, lnT, lnT2, lnT4);
@@ -293,11 +322,13 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         }
         sk[i] += se + so;
       }
-    }
-    // first touch of this row block's sums: later row blocks add their column contributions
+      if (h == KX_SPLIT - 1) {
+        // first touch of this row block's sums: later row blocks add their column contributions
 #pragma unroll
-    for (int i = 0; i < KX_TB; i++) KX_S_STORE(kb * KX_TB + i, sk[i]);
-    advance();
+        for (int i = 0; i < KX_TB; i++) KX_S_STORE(kb * KX_TB + i, sk[i]);
+      }
+      advance();
+    }
   }
 
   // ---- rho * D_km  (mix_transport.py:621-622 and transportProps.okl:43-47; p and Mbar cancel) ----
