@@ -332,6 +332,42 @@ def test_fit_rcp_diff_coeffs_option(kinetix):
     assert rel_err(rhoD, d_rrd) > 1e-8
 
 
+def test_batch_beyond_32bit_element_indices(kinetix):
+    """(N+1) * n_states > 2^31: the reference's `int` indexing (productionRates.okl:27,49; bk.cpp:29) overflows at
+    39.7 M GRI states; here offsets are 64-bit.  The last states of a 41 M batch must match the oracle."""
+    mech = 'gri30'
+    N = _setup(kinetix, mech)
+    S = 41_000_000
+    assert (N + 1) * S > 2 ** 31
+    free, _ = torch.cuda.mem_get_info()
+    if free < 2.2 * (N + 1) * S * 8:
+        pytest.skip('not enough device memory for the 41 M state batch')
+    n_tail = 2048
+    tail = synthetic_states(N, n_tail, seed=404)
+    d_state = torch.empty((N + 1, S), dtype=torch.float64, device='cuda')
+    d_state[0].fill_(1500.0)
+    d_state[1:].fill_(1.0 / N)
+    d_state[:, S - n_tail:] = torch.from_numpy(tail).cuda()
+    d_rates = torch.empty_like(d_state)
+    kinetix.productionRates(S, S, S, 1.0, d_state, d_rates)
+    torch.cuda.synchronize()
+    new = d_rates[:, S - n_tail:].cpu().numpy()
+    ref = Oracle(mech).production_rates(tail, P_ATM)
+    rate_err, hrr_err = bk1_errors(new, ref)
+    assert rate_err <= TOL and hrr_err <= TOL
+    # BK2 on the same slab (rho*D rows reuse the rates buffer)
+    visc = torch.empty(S, dtype=torch.float64, device='cuda')
+    cond = torch.empty_like(visc)
+    rhoD = d_rates[1:]
+    kinetix.mixtureAvgTransportProps(S, S, S, 1.0, d_state, visc, cond, rhoD)
+    torch.cuda.synchronize()
+    rc, rv, rrd = Oracle(mech).transport(tail, 1.0)
+    assert rel_err(cond[S - n_tail:].cpu().numpy(), rc) <= TOL
+    assert rel_err(rhoD[:, S - n_tail:].cpu().numpy(), rrd) <= TOL
+    del d_state, d_rates, visc, cond
+    torch.cuda.empty_cache()
+
+
 def test_errors_are_loud(kinetix):
     kinetix.finalize()
     with pytest.raises(kinetix.KinetixError):
