@@ -41,6 +41,271 @@ def choose_tile(N, forced=None):
     return best[1], best[2]
 
 
+
+def _emit_bk2_single(out, mech, fits, opt, options, sp, rsize, tq):
+    """Tables + macros for csrc/kx_bk2.cuh (one thread per state).  Returns (dynamic smem bytes, states per CTA)."""
+    N = mech.n_species
+    M = mech.molar_masses
+    tb, NP = choose_tile(N, opt.get('tile_bk2'))
+    NB = NP // tb
+    align = 16 // rsize                            # chunk sizes are multiples of 16 bytes (bulk copy)
+    wchunk = -(-(N * tb) // align) * align         # reals per Wilke chunk
+    dchunk = -(-(tb * tb * 6) // align) * align    # reals per diffusion tile
+    limit = 227 * 1024 - 1024
+    n_arrays = 1 if opt['bk2_scratch'] else 2      # [k][thread] arrays in shared memory: X (+ b_k / S_k)
+    explicit = 'block_bk2' in (options or {}) or 'minb_bk2' in (options or {})
+    max_block = opt['block_bk2'] * (2 if sp and 'block_bk2' not in (options or {}) else 1)
+
+    def plan(split):
+        """(resident threads, CTAs/SM, block, split, r0, j0, chunk_max) for a streaming granularity: whole
+        table blocks (split 1) or half blocks (split 2: tile rows [0,r0)/[r0,tb), Wilke columns [0,j0)/[j0,N),
+        all sub-chunks 16-byte multiples)."""
+        r0 = j0 = 0
+        if split == 2:
+            r0 = next((r for r in range((tb + 1) // 2, tb) if (r * tb * 6) % align == 0), 0)
+            j0 = next((j for j in range((N + 1) // 2, N) if (j * tb) % align == 0), 0)
+            if not r0 or not j0:
+                return None
+            cmax = max(r0 * tb * 6, dchunk - r0 * tb * 6, j0 * tb, wchunk - j0 * tb)
+        else:
+            cmax = max(wchunk, dchunk)
+        best = None
+        for minb in ((opt['minb_bk2'],) if explicit else (2, 1)):
+            top = max_block if explicit else (256 if minb == 2 else 512)
+            for b in range(min(top, 1024), 31, -32):
+                smem = 16 + (2 * cmax + n_arrays * NP * b) * rsize
+                if smem * minb + 1024 * (minb - 1) <= limit and b * minb <= 640:
+                    cand = (b * minb, minb, b, split, r0, j0, cmax)
+                    if best is None or cand > best:
+                        best = cand
+                    break
+        return best
+
+    # occupancy: as many resident threads per SM as shared memory allows.  Half-block streaming halves the
+    # staging buffers, which is what lets two CTAs share an SM (decoupled barriers / prologues: +45 % on the
+    # 9-species mechanism); with a single CTA per SM it only adds barriers, so whole blocks are kept then.
+    plans = [p for p in (plan(s_) for s_ in ((opt['bk2_split'],) if opt['bk2_split'] == 1 else (2, 1))) if p]
+    two = [p for p in plans if p[1] >= 2 and p[3] == 2]
+    one = [p for p in plans if p[3] == 1]
+    chosen = max(two) if two and (not one or max(two)[0] >= max(one)[0]) else max(one or plans)
+    _, opt['minb_bk2'], block2, split, r0, j0, chunk_max = chosen
+
+    def smem_for(b):
+        return 16 + (2 * chunk_max + n_arrays * NP * b) * rsize
+
+    bk2_smem = smem_for(block2)
+    opt['block_bk2'] = block2
+    out.append(f'#define KX_TB {tb}')
+    out.append(f'#define KX_NP {NP}')
+    out.append(f'#define KX_BK2_BLOCK {block2}')
+    out.append(f'#define KX_BK2_MINB {opt["minb_bk2"]}')
+    out.append(f'#define KX_BK2_SCRATCH {1 if opt["bk2_scratch"] else 0}')
+    out.append(f'#define KX_SPLIT {split}')
+    out.append(f'#define KX_R0 {r0}')
+    out.append(f'#define KX_J0 {j0}')
+    out.append(f'#define KX_CHUNK_MAX {chunk_max}')
+    out.append(f'#define KX_WCHUNK {wchunk}')
+    out.append(f'#define KX_DCHUNK {dchunk}')
+    out.append(_table('kx_m4', [m ** -0.25 for m in M]))
+    out.append(_table('kx_cond', [c for k in range(N) for c in fits.conductivity[k]], qualifier=tq, dims=f'[{N}][5]'))
+    out.append(_table('kx_visc', [c for k in range(N) for c in fits.viscosity[k]], qualifier=tq, dims=f'[{N}][5]'))
+    # Wilke mass factors c_kj = 1/sqrt(8 (1 + M_k/M_j)), one chunk per k-block: [kb][j][i], k = kb*tb + i
+    wil = []
+    for kb in range(NB):
+        chunk = []
+        for j in range(N):
+            for i in range(tb):
+                k = kb * tb + i
+                chunk.append(1.0 / math.sqrt(8.0 * (1.0 + M[k] / M[j])) if k < N else 0.0)
+        chunk += [0.0] * (wchunk - len(chunk))
+        wil += chunk
+    out.append(_table('kx_wilke', wil, qualifier='__device__ const __align__(16)'))
+    # binary diffusion quartics, lower-triangular tiles; padded pairs evaluate to D = 1
+    rcp = fits.reciprocal_diffusivity
+    dif = []
+    for kb in range(NB):
+        for jb in range(kb + 1):
+            for i in range(tb):
+                for j in range(tb):
+                    k, jj = kb * tb + i, jb * tb + j
+                    if k < N and jj < N and k > jj:
+                        dif += list(fits.diffusivity[k][jj]) + [0.0]
+                    else:
+                        dif += [1.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+            dif += [0.0] * (dchunk - tb * tb * 6)
+    out.append(f'#define KX_RCP_DIFF {1 if rcp else 0}')
+    out.append(_table('kx_diff', dif, qualifier='__device__ const __align__(16)'))
+    out.append('#include "kx_bk2.cuh"')
+    return bk2_smem, block2
+
+
+def choose_tile_lanes(N, lanes, forced=None):
+    """Tile edge (a multiple of `lanes`) minimising the pair slots evaluated per state: off-diagonal tiles are
+    full, a diagonal tile row i costs ceil(i / lanes) slots per lane."""
+    best = None
+    for tb in ([forced] if forced else (6, 8, 10, 12, 4)):
+        if tb % lanes:
+            continue
+        NP = -(-N // tb) * tb
+        NB = NP // tb
+        diag = sum(-(-i // lanes) for i in range(1, tb)) * lanes
+        slots = NB * (NB - 1) // 2 * tb * tb + NB * diag
+        cost = slots + 3 * NP * NP / 10.0          # + Wilke terms (3 DFMA vs ~10 per pair slot)
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, tb, NP)
+    return best[1], best[2]
+
+
+def _emit_bk2_lanes(out, mech, fits, opt, lanes, rsize, tq):
+    """Tables + macros for csrc/kx_bk2_lanes.cuh (`lanes` threads per state).  Returns (smem bytes, states per CTA)."""
+    N = mech.n_species
+    M = mech.molar_masses
+    tb, NP = choose_tile_lanes(N, lanes, opt.get('tile_bk2'))
+    NB = NP // tb
+    align = 16 // rsize
+    wchunk = -(-(NP * tb) // align) * align
+    dchunk = -(-(tb * tb * 6) // align) * align
+    cmax = max(wchunk, dchunk)
+    limit = 227 * 1024
+    max_threads = opt.get('bk2_max_threads', 512)
+    stages = opt.get('bk2_stages') or (4 if 4 * cmax * rsize <= 16 * 1024 else 2)
+
+    spt = opt.get('bk2_spt', 1)                    # states per lane group
+
+    def fit(stg):
+        states = (limit - 16 * stg - stg * cmax * rsize) // (2 * NP * rsize)
+        return min(states * lanes // spt, max_threads, 1024) // 32 * 32
+    threads = fit(stages)
+    if stages > 2 and fit(2) > threads and threads < max_threads:
+        stages, threads = 2, fit(2)                # the ring must not cost a warp
+    threads = opt.get('bk2_threads', threads)
+    states = threads // lanes * spt
+    smem = 16 * stages + (stages * cmax + 2 * NP * (states // spt if opt.get('bk2_alias') else states)) * rsize
+    if opt.get('bk2_alias'):
+        out.append('#define KX_WHATIF_ALIAS 1')
+    out.append(f'#define KX_TB {tb}')
+    out.append(f'#define KX_NP {NP}')
+    out.append(f'#define KX_L {lanes}')
+    out.append(f'#define KX_P {spt}')
+    out.append(f'#define KX_BK2_BLOCK {threads}')
+    out.append(f'#define KX_STAGES {stages}')
+    out.append(f'#define KX_CHUNK_MAX {cmax}')
+    out.append(f'#define KX_WCHUNK {wchunk}')
+    out.append(f'#define KX_DCHUNK {dchunk}')
+    # one 16-real record per species: {1/M, M, M^-1/4, -, cond[0..4], -, visc[0..4], -}
+    sptab = []
+    for k in range(NP):
+        if k < N:
+            sptab += [1. / M[k], M[k], M[k] ** -0.25, 0.0] + list(fits.conductivity[k]) + [0.0] + list(fits.viscosity[k]) + [0.0]
+        else:
+            sptab += [0.0, 0.0, 1.0, 0.0] + [1.0, 0, 0, 0, 0, 0] + [1.0, 0, 0, 0, 0, 0]
+    out.append(_table('kx_sptab', sptab, qualifier='__device__ const __align__(16)'))
+    # Wilke mass factors c_kj = 1/sqrt(8 (1 + M_k/M_j)), one chunk per k-block: [kb][j][i], k = kb*tb + i, j < NP
+    wil = []
+    for kb in range(NB):
+        chunk = []
+        for j in range(NP):
+            for i in range(tb):
+                k = kb * tb + i
+                chunk.append(1.0 / math.sqrt(8.0 * (1.0 + M[k] / M[j])) if (k < N and j < N) else 0.0)
+        chunk += [0.0] * (wchunk - len(chunk))
+        wil += chunk
+    out.append(_table('kx_wilke', wil, qualifier='__device__ const __align__(16)'))
+    # binary diffusion quartics, lower-triangular tiles; padded pairs evaluate to D = 1
+    dif = []
+    for kb in range(NB):
+        for jb in range(kb + 1):
+            for i in range(tb):
+                for j in range(tb):
+                    k, jj = kb * tb + i, jb * tb + j
+                    if k < N and jj < N and k > jj:
+                        dif += list(fits.diffusivity[k][jj]) + [0.0]
+                    else:
+                        dif += [1.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+            dif += [0.0] * (dchunk - tb * tb * 6)
+    out.append(f'#define KX_RCP_DIFF {1 if fits.reciprocal_diffusivity else 0}')
+    out.append(_table('kx_diff', dif, qualifier='__device__ const __align__(16)'))
+    out.append('#include "kx_bk2_lanes.cuh"')
+    return smem, states
+
+
+def _emit_bk2_tmem(out, mech, fits, opt, tq):
+    """Tables + macros for csrc/kx_bk2_tmem.cuh (two states per thread, S_k in tensor memory, FP64).
+    Returns (smem bytes, states per CTA) or None when the mechanism does not fit the layout."""
+    N = mech.n_species
+    M = mech.molar_masses
+    spt = opt.get('bk2_spt', 2)
+    tb, NP = choose_tile(N, opt.get('tile_bk2'))
+    NB = NP // tb
+    wchunk = -(-(NP * tb) // 2) * 2
+    dchunk = -(-(tb * tb * 6) // 2) * 2
+    cmax = max(wchunk, dchunk)
+    limit = 227 * 1024
+    ns = -(-NP // 8) * 8                           # doubles reserved per state in tensor memory
+    plan = None
+    for threads in (256, 128):
+        if (threads // 128) * spt * 2 * ns > 512:  # columns per TMEM lane
+            continue
+        for stages in ((opt['bk2_stages'],) if opt.get('bk2_stages') else (4, 2)):
+            smem = 16 * stages + 16 + (stages * cmax + NP * threads * spt) * 8
+            if smem <= limit:
+                plan = (threads, stages, smem)
+                break
+        if plan:
+            break
+    if plan is None or plan[0] < opt.get('bk2_tmem_min_threads', 256):
+        return None
+    threads, stages, smem = plan
+    out.append(f'#define KX_TB {tb}')
+    out.append(f'#define KX_NP {NP}')
+    out.append(f'#define KX_P {spt}')
+    out.append(f'#define KX_NS {ns}')
+    out.append(f'#define KX_BK2_BLOCK {threads}')
+    out.append(f'#define KX_STAGES {stages}')
+    out.append(f'#define KX_CHUNK_MAX {cmax}')
+    out.append(f'#define KX_WCHUNK {wchunk}')
+    out.append(f'#define KX_DCHUNK {dchunk}')
+    out.append(_table('kx_m4', [m ** -0.25 for m in M]))
+    out.append(_table('kx_cond', [c for k in range(N) for c in fits.conductivity[k]], qualifier=tq, dims=f'[{N}][5]'))
+    out.append(_table('kx_visc', [c for k in range(N) for c in fits.viscosity[k]], qualifier=tq, dims=f'[{N}][5]'))
+    out.append(_table('kx_wilke', _wilke_chunks(M, N, NP, tb, wchunk), qualifier='__device__ const __align__(16)'))
+    out.append(f'#define KX_RCP_DIFF {1 if fits.reciprocal_diffusivity else 0}')
+    out.append(_table('kx_diff', _diff_tiles(fits, N, NP, tb, dchunk), qualifier='__device__ const __align__(16)'))
+    out.append('#include "kx_bk2_tmem.cuh"')
+    return smem, threads * spt
+
+
+def _wilke_chunks(M, N, NP, tb, wchunk):
+    """Wilke mass factors c_kj = 1/sqrt(8 (1 + M_k/M_j)), one chunk per k-block: [kb][j][i], k = kb*tb + i, j < NP."""
+    wil = []
+    for kb in range(NP // tb):
+        chunk = []
+        for j in range(NP):
+            for i in range(tb):
+                k = kb * tb + i
+                chunk.append(1.0 / math.sqrt(8.0 * (1.0 + M[k] / M[j])) if (k < N and j < N) else 0.0)
+        chunk += [0.0] * (wchunk - len(chunk))
+        wil += chunk
+    return wil
+
+
+def _diff_tiles(fits, N, NP, tb, dchunk):
+    """Binary diffusion quartics, lower-triangular tiles (kb >= jb), 5 coefficients + pad per pair; padded pairs
+    evaluate to D = 1."""
+    dif = []
+    for kb in range(NP // tb):
+        for jb in range(kb + 1):
+            for i in range(tb):
+                for j in range(tb):
+                    k, jj = kb * tb + i, jb * tb + j
+                    if k < N and jj < N and k > jj:
+                        dif += list(fits.diffusivity[k][jj]) + [0.0]
+                    else:
+                        dif += [1.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+            dif += [0.0] * (dchunk - tb * tb * 6)
+    return dif
+
+
 def emit_module(mech, fits, options=None, single_precision=False):
     """Return the CUDA source text.  `fits` is a TransportFits or None (BK2 omitted).
     single_precision: FP32 arithmetic; the module then serves FP64 buffers ("fpmix") and FP32 buffers."""
@@ -112,97 +377,25 @@ def emit_module(mech, fits, options=None, single_precision=False):
 
     has_bk2 = fits is not None
     bk2_smem = 0
+    bk2_states_per_cta = 0
     if has_bk2:
-        tb, NP = choose_tile(N, opt.get('tile_bk2'))
-        NB = NP // tb
-        align = 16 // rsize                            # chunk sizes are multiples of 16 bytes (bulk copy)
-        wchunk = -(-(N * tb) // align) * align         # reals per Wilke chunk
-        dchunk = -(-(tb * tb * 6) // align) * align    # reals per diffusion tile
         limit = 227 * 1024 - 1024
-        n_arrays = 1 if opt['bk2_scratch'] else 2      # [k][thread] arrays in shared memory: X (+ b_k / S_k)
-        explicit = 'block_bk2' in (options or {}) or 'minb_bk2' in (options or {})
-        max_block = opt['block_bk2'] * (2 if sp and 'block_bk2' not in (options or {}) else 1)
-
-        def plan(split):
-            """(resident threads, CTAs/SM, block, split, r0, j0, chunk_max) for a streaming granularity: whole
-            table blocks (split 1) or half blocks (split 2: tile rows [0,r0)/[r0,tb), Wilke columns [0,j0)/[j0,N),
-            all sub-chunks 16-byte multiples)."""
-            r0 = j0 = 0
-            if split == 2:
-                r0 = next((r for r in range((tb + 1) // 2, tb) if (r * tb * 6) % align == 0), 0)
-                j0 = next((j for j in range((N + 1) // 2, N) if (j * tb) % align == 0), 0)
-                if not r0 or not j0:
-                    return None
-                cmax = max(r0 * tb * 6, dchunk - r0 * tb * 6, j0 * tb, wchunk - j0 * tb)
-            else:
-                cmax = max(wchunk, dchunk)
-            best = None
-            for minb in ((opt['minb_bk2'],) if explicit else (2, 1)):
-                top = max_block if explicit else (256 if minb == 2 else 512)
-                for b in range(min(top, 1024), 31, -32):
-                    smem = 16 + (2 * cmax + n_arrays * NP * b) * rsize
-                    if smem * minb + 1024 * (minb - 1) <= limit and b * minb <= 640:
-                        cand = (b * minb, minb, b, split, r0, j0, cmax)
-                        if best is None or cand > best:
-                            best = cand
-                        break
-            return best
-
-        # occupancy: as many resident threads per SM as shared memory allows.  Half-block streaming halves the
-        # staging buffers, which is what lets two CTAs share an SM (decoupled barriers / prologues: +45 % on the
-        # 9-species mechanism); with a single CTA per SM it only adds barriers, so whole blocks are kept then.
-        plans = [p for p in (plan(s_) for s_ in ((opt['bk2_split'],) if opt['bk2_split'] == 1 else (2, 1))) if p]
-        two = [p for p in plans if p[1] >= 2 and p[3] == 2]
-        one = [p for p in plans if p[3] == 1]
-        chosen = max(two) if two and (not one or max(two)[0] >= max(one)[0]) else max(one or plans)
-        _, opt['minb_bk2'], block2, split, r0, j0, chunk_max = chosen
-
-        def smem_for(b):
-            return 16 + (2 * chunk_max + n_arrays * NP * b) * rsize
-
-        bk2_smem = smem_for(block2)
-        opt['block_bk2'] = block2
-        out.append(f'#define KX_TB {tb}')
-        out.append(f'#define KX_NP {NP}')
-        out.append(f'#define KX_BK2_BLOCK {block2}')
-        out.append(f'#define KX_BK2_MINB {opt["minb_bk2"]}')
-        out.append(f'#define KX_BK2_SCRATCH {1 if opt["bk2_scratch"] else 0}')
-        out.append(f'#define KX_SPLIT {split}')
-        out.append(f'#define KX_R0 {r0}')
-        out.append(f'#define KX_J0 {j0}')
-        out.append(f'#define KX_CHUNK_MAX {chunk_max}')
-        out.append(f'#define KX_WCHUNK {wchunk}')
-        out.append(f'#define KX_DCHUNK {dchunk}')
-        out.append(_table('kx_m4', [m ** -0.25 for m in M]))
-        out.append(_table('kx_cond', [c for k in range(N) for c in fits.conductivity[k]], qualifier=tq, dims=f'[{N}][5]'))
-        out.append(_table('kx_visc', [c for k in range(N) for c in fits.viscosity[k]], qualifier=tq, dims=f'[{N}][5]'))
-        # Wilke mass factors c_kj = 1/sqrt(8 (1 + M_k/M_j)), one chunk per k-block: [kb][j][i], k = kb*tb + i
-        wil = []
-        for kb in range(NB):
-            chunk = []
-            for j in range(N):
-                for i in range(tb):
-                    k = kb * tb + i
-                    chunk.append(1.0 / math.sqrt(8.0 * (1.0 + M[k] / M[j])) if k < N else 0.0)
-            chunk += [0.0] * (wchunk - len(chunk))
-            wil += chunk
-        out.append(_table('kx_wilke', wil, qualifier='__device__ const __align__(16)'))
-        # binary diffusion quartics, lower-triangular tiles; padded pairs evaluate to D = 1
-        rcp = fits.reciprocal_diffusivity
-        dif = []
-        for kb in range(NB):
-            for jb in range(kb + 1):
-                for i in range(tb):
-                    for j in range(tb):
-                        k, jj = kb * tb + i, jb * tb + j
-                        if k < N and jj < N and k > jj:
-                            dif += list(fits.diffusivity[k][jj]) + [0.0]
-                        else:
-                            dif += [1.0, 0.0, 0.0, 0.0, 0.0, 0.0]
-                dif += [0.0] * (dchunk - tb * tb * 6)
-        out.append(f'#define KX_RCP_DIFF {1 if rcp else 0}')
-        out.append(_table('kx_diff', dif, qualifier='__device__ const __align__(16)'))
-        out.append('#include "kx_bk2.cuh"')
+        align = 16 // rsize                            # chunk sizes are multiples of 16 bytes (bulk copy)
+        # lanes per state (csrc/kx_bk2_lanes.cuh): shared memory holds 2 NP reals per state, so large mechanisms
+        # get few resident states per SM; 2 or 4 lanes per state bring the resident warps back up
+        lanes = opt.get('bk2_lanes')
+        if lanes is None:
+            states_1 = (limit - 8 * 1024) // (2 * (N + 3) * rsize)
+            lanes = 1 if states_1 >= 384 else (2 if states_1 >= 192 else 4)
+        planned = None
+        if opt.get('bk2_tmem') and not sp:
+            planned = _emit_bk2_tmem(out, mech, fits, opt, tq)
+        if planned:
+            bk2_smem, bk2_states_per_cta = planned
+        elif lanes > 1 or opt.get('bk2_spt', 1) > 1 or opt.get('bk2_ring'):
+            bk2_smem, bk2_states_per_cta = _emit_bk2_lanes(out, mech, fits, opt, lanes, rsize, tq)
+        else:
+            bk2_smem, bk2_states_per_cta = _emit_bk2_single(out, mech, fits, opt, options, sp, rsize, tq)
 
     names = ' '.join(mech.species_names)
     out.append(f'''
@@ -275,14 +468,14 @@ static int launch_thermo(long long n, long long offsetT, long long offset, doubl
 template <typename S>
 static int launch_bk2(long long n, long long offsetT, long long offset, double pressure, const void* state,
                       void* conductivity, void* viscosity, void* rhoD, double Tref, cudaStream_t stream) {{
-  const int block = KX_BK2_BLOCK;
+  const int block = KX_BK2_BLOCK, per_cta = {bk2_states_per_cta};   // states per CTA
   const size_t smem = {bk2_smem};
   static bool configured = false;
   if (!configured) {{
     if (int e = kxm_set_smem(kx_bk2<S>, smem)) return e;
     configured = true;
   }}
-  const unsigned grid = (unsigned)((n + block - 1) / block);
+  const unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
   kx_bk2<S><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
                                            (S*)viscosity, (S*)rhoD, Tref);
   return (int)cudaGetLastError();

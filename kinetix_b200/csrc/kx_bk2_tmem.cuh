@@ -1,0 +1,479 @@
+// kx_bk2_tmem.cuh -- BK2 (mixture-averaged conductivity, viscosity, rho*D_km): KX_P states per thread, the
+// per-state sums S_k in TENSOR MEMORY, the mole fractions X_k in shared memory.  FP64 only.
+//
+// Same arithmetic as csrc/kx_bk2.cuh (reference benchmark/okl/transportProps.okl:11-49 around
+// kinetix/core/mix_transport.py:474-626).  What changed, and why (profiles/ncu_r01_bk2_*.txt):
+//   * The one-state-per-thread kernel is bound by the shared-memory data pipe, not by the FP64 pipe: every
+//     species pair costs 3 LDS.128 (the quartic's coefficients, a broadcast) = 6 LSU wavefronts per warp against
+//     9 DFMA; in the pair loops the LSU pipe is the busier one (65 % of peak overall, FP64 58 %).  Replacing the
+//     coefficient loads by register moves (timing experiment) gave 739 instead of 446 M states/s.
+//   * So every coefficient fetched from shared memory is used for KX_P = 2 states here: half the wavefronts per
+//     state.  A thread then needs both states' vectors on chip, and shared memory (227 KB) only holds X_k AND
+//     S_k for 256 GRI-3.0 states per SM, i.e. 4 warps of two-state threads -- too few to cover latencies.
+//   * Blackwell's tensor memory is 256 KB per SM that this kernel would leave idle.  It is addressed as
+//     128 lanes x 512 32-bit columns, and warp w may touch lanes 32 (w % 4) .. +31: exactly a per-thread
+//     scratchpad.  The S_k of all 512 resident states live there (thread = lane, 2 * KX_NS columns per state,
+//     tcgen05.st / tcgen05.ld 32x32b, SASS STTM / LDTM), the X_k stay in shared memory as [k][state]: 8 warps
+//     of two-state threads per SM, and the S_k traffic (b_j in the Wilke sums, the read-modify-write of the
+//     column sums per tile) moves off the LSU pipe onto the otherwise unused TMEM datapath.
+//   * The table stream (Wilke k-blocks, then diffusion tiles) goes through a KX_STAGES-deep ring of TMA bulk
+//     copies with full/empty mbarriers (no CTA-wide barrier per chunk).
+//   * State rows are loaded in fully unrolled batches of 32 independent loads per state.
+//
+// The including translation unit defines KX_N, KX_NP (multiple of KX_TB), KX_TB, KX_P, KX_BK2_BLOCK (threads;
+// a multiple of 128 so that the warps spread evenly over the four TMEM lane quadrants), KX_NS (doubles reserved
+// per state in TMEM, >= KX_NP), KX_STAGES, KX_CHUNK_MAX, KX_WCHUNK (= KX_NP * KX_TB), KX_DCHUNK (= KX_TB^2 * 6),
+// KX_RCP_DIFF and the tables
+//   __constant__ double kx_rcpM[KX_N], kx_M[KX_N], kx_m4[KX_N], kx_cond[KX_N][5], kx_visc[KX_N][5]
+//   __device__   double kx_wilke[KX_NB][KX_WCHUNK]   c_kj as [kb][j][i], k = kb*TB + i, j < KX_NP (zero padded)
+//   __device__   double kx_diff[n_tiles][KX_DCHUNK]  lower-triangular tiles, row-major over (kb, jb); 5 coefs + pad
+#pragma once
+#include <cstdint>
+#include "kx_math.cuh"
+#include "kx_pipe.cuh"
+
+#define KX_NB (KX_NP / KX_TB)
+#define KX_N_DTILES (KX_NB * (KX_NB + 1) / 2)
+static_assert(sizeof(real) == 8, "the tensor-memory BK2 kernel is FP64 only");
+
+KX_DEVICE real kx_quartic(const real* __restrict__ c, real l)
+{
+  return fma(fma(fma(fma(c[4], l, c[3]), l, c[2]), l, c[1]), l, c[0]);
+}
+KX_DEVICE const real* kx_chunk_src(int c)
+{
+  return c < KX_NB ? kx_wilke + (size_t)c * KX_WCHUNK : kx_diff + (size_t)(c - KX_NB) * KX_DCHUNK;
+}
+KX_DEVICE unsigned kx_chunk_bytes(int c) { return (unsigned)((c < KX_NB ? KX_WCHUNK : KX_DCHUNK) * sizeof(real)); }
+
+// ---- tensor memory as a per-thread scratchpad ------------------------------------------------------
+// 32x32b shape: lane i of the warp reads / writes N consecutive 32-bit columns of TMEM lane (quadrant base + i).
+// All accesses are warp-uniform in their column address.  Loads are asynchronous: the destination registers
+// are valid after kx_tm_wait_ld(); kx_tm_unpack() pins the consumers behind that wait for the compiler.
+#define KX_TM_LD(N, REGS, ...)                                                                                  \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x" #N ".b32 {" REGS "}, [%" #N "];" : __VA_ARGS__ : "r"(taddr))
+KX_DEVICE void kx_tm_ld2(unsigned taddr, unsigned* r)
+{
+  KX_TM_LD(2, "%0,%1", "=r"(r[0]), "=r"(r[1]));
+}
+KX_DEVICE void kx_tm_ld4(unsigned taddr, unsigned* r)
+{
+  KX_TM_LD(4, "%0,%1,%2,%3", "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]));
+}
+KX_DEVICE void kx_tm_ld8(unsigned taddr, unsigned* r)
+{
+  KX_TM_LD(8, "%0,%1,%2,%3,%4,%5,%6,%7", "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+           "=r"(r[6]), "=r"(r[7]));
+}
+KX_DEVICE void kx_tm_ld16(unsigned taddr, unsigned* r)
+{
+  KX_TM_LD(16, "%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15", "=r"(r[0]), "=r"(r[1]), "=r"(r[2]),
+           "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]));
+}
+KX_DEVICE void kx_tm_st2(unsigned taddr, const unsigned* r)
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+KX_DEVICE void kx_tm_st4(unsigned taddr, const unsigned* r)
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+KX_DEVICE void kx_tm_st8(unsigned taddr, const unsigned* r)
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+KX_DEVICE void kx_tm_st16(unsigned taddr, const unsigned* r)
+{
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+KX_DEVICE void kx_tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+KX_DEVICE void kx_tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// issue the loads of N consecutive doubles (column `taddr`, 2 columns per double) in pieces of 8 / 4 / 2 / 1
+template <int N, int OFF = 0>
+KX_DEVICE void kx_tm_load(unsigned taddr, unsigned* r)
+{
+  if constexpr (N >= 8) {
+    kx_tm_ld16(taddr + 2 * OFF, r + 2 * OFF);
+    kx_tm_load<N - 8, OFF + 8>(taddr, r);
+  } else if constexpr (N >= 4) {
+    kx_tm_ld8(taddr + 2 * OFF, r + 2 * OFF);
+    kx_tm_load<N - 4, OFF + 4>(taddr, r);
+  } else if constexpr (N >= 2) {
+    kx_tm_ld4(taddr + 2 * OFF, r + 2 * OFF);
+    kx_tm_load<N - 2, OFF + 2>(taddr, r);
+  } else if constexpr (N == 1) {
+    kx_tm_ld2(taddr + 2 * OFF, r + 2 * OFF);
+  }
+}
+// after kx_tm_wait_ld(): turn the raw registers into doubles (the empty asm keeps every use behind the wait)
+template <int N>
+KX_DEVICE void kx_tm_unpack(unsigned (&r)[2 * N], real (&d)[N])
+{
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    asm volatile("" : "+r"(r[2 * i]), "+r"(r[2 * i + 1]));
+    d[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+  }
+}
+template <int N, int OFF = 0>
+KX_DEVICE void kx_tm_store_raw(unsigned taddr, const unsigned* r)
+{
+  if constexpr (N >= 8) {
+    kx_tm_st16(taddr + 2 * OFF, r + 2 * OFF);
+    kx_tm_store_raw<N - 8, OFF + 8>(taddr, r);
+  } else if constexpr (N >= 4) {
+    kx_tm_st8(taddr + 2 * OFF, r + 2 * OFF);
+    kx_tm_store_raw<N - 4, OFF + 4>(taddr, r);
+  } else if constexpr (N >= 2) {
+    kx_tm_st4(taddr + 2 * OFF, r + 2 * OFF);
+    kx_tm_store_raw<N - 2, OFF + 2>(taddr, r);
+  } else if constexpr (N == 1) {
+    kx_tm_st2(taddr + 2 * OFF, r + 2 * OFF);
+  }
+}
+template <int N>
+KX_DEVICE void kx_tm_store(unsigned taddr, const real (&d)[N])
+{
+  unsigned r[2 * N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    r[2 * i] = (unsigned)__double2loint(d[i]);
+    r[2 * i + 1] = (unsigned)__double2hiint(d[i]);
+  }
+  kx_tm_store_raw<N>(taddr, r);
+}
+
+template <typename ST>   // ST: storage type of the state / result buffers (reference: dfloat)
+__global__ void __launch_bounds__(KX_BK2_BLOCK, 1)
+kx_bk2(const long long n_states, const long long offsetT, const long long offset, const real pressure,
+       const ST* __restrict__ state, ST* __restrict__ conductivity, ST* __restrict__ viscosity,
+       ST* __restrict__ rhoD, const double Tref)
+{
+  extern __shared__ __align__(16) unsigned char kx_sm_raw[];
+  // G threads, every thread carries P states (slots t, t + G, ...): LD = G * P states per CTA
+  constexpr int P = KX_P, G = KX_BK2_BLOCK, LD = G * P, TB = KX_TB;
+  constexpr int NW = KX_BK2_BLOCK / 32, STG = KX_STAGES;
+  constexpr int N_CHUNKS = KX_NB + KX_N_DTILES;
+  constexpr int TM_COLS = (NW / 4) * P * 2 * KX_NS;   // columns in use per TMEM lane
+  static_assert((STG & (STG - 1)) == 0 && KX_BK2_BLOCK % 128 == 0 && TM_COLS <= 512 && KX_NS >= KX_NP, "shape");
+  uint64_t* const full = reinterpret_cast<uint64_t*>(kx_sm_raw);           // STG full + STG empty barriers
+  uint64_t* const empty = full + STG;
+  unsigned* const tm_base_slot = reinterpret_cast<unsigned*>(empty + STG);  // TMEM base address (16 bytes reserved)
+  real* const buf0 = reinterpret_cast<real*>(kx_sm_raw + 16 * STG + 16);   // STG x KX_CHUNK_MAX reals
+  real* __restrict__ X = buf0 + STG * KX_CHUNK_MAX + threadIdx.x;          // X[k] of state p at X[k * LD + p * G]
+  const int warp = threadIdx.x >> 5;
+
+  if (warp == 0) {
+    // all 512 columns: this CTA is alone on its SM (shared memory), nobody else needs tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(kx_smem_addr(tm_base_slot))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STG; s++) { kx_mbar_init(&full[s], 1); kx_mbar_init(&empty[s], NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < STG; s++)
+      if (s < N_CHUNKS) kx_bulk_load(buf0 + s * KX_CHUNK_MAX, kx_chunk_src(s), kx_chunk_bytes(s), &full[s]);
+  }
+
+  bool live[P];
+  long long id[P];
+  real lnT[P], lnT2[P], lnT4[P], sqrT[P], Mbar[P];
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    const long long gid = (long long)blockIdx.x * LD + p * G + threadIdx.x;
+    live[p] = gid < n_states;
+    id[p] = live[p] ? gid : n_states - 1;   // tail slots recompute the last state, store nothing
+  }
+
+  // ---- mole fractions (transportProps.okl:23-35): batches of 32 independent row loads per state ----
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    const ST* sp = state + id[p] + offsetT;
+    const ST t_raw = kx_ld_stream(state + id[p]);
+    real acc = 0;
+    constexpr int LB = 32;
+#pragma unroll
+    for (int k0 = 0; k0 < KX_N; k0 += LB) {
+      ST y[LB];
+#pragma unroll
+      for (int i = 0; i < LB; i++)
+        if (k0 + i < KX_N) y[i] = kx_ld_stream(sp + (size_t)(k0 + i) * offset);
+#pragma unroll
+      for (int i = 0; i < LB; i++) {
+        if (k0 + i < KX_N) {
+          const real yi = (real)y[i];
+          const real w = (yi > (real)0 ? yi : (real)0) * kx_rcpM[k0 + i];
+          X[(k0 + i) * LD + p * G] = w;
+          acc += w;
+        }
+      }
+    }
+    Mbar[p] = kx_rcp(acc);
+    const double Td = Tref * (double)t_raw;
+    lnT[p] = (real)kx_log(Td);
+    sqrT[p] = kx_sqrt((real)Td);
+    lnT2[p] = lnT[p] * lnT[p];
+    lnT4[p] = lnT2[p] * lnT2[p];
+  }
+
+  // TMEM base address: visible after the allocating warp's write + CTA barrier
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();   // also: mbarrier inits visible to all threads before the first wait
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // this thread's S_k of state p: lane quadrant (warp % 4), column (2 KX_NS) ((warp / 4) P + p) + 2 k
+  const unsigned tm0 = *reinterpret_cast<volatile unsigned*>(tm_base_slot) + ((unsigned)(warp & 3) << 21) +
+                       (unsigned)((warp >> 2) * P * 2 * KX_NS);
+#define KX_TM(p, k) (tm0 + (unsigned)((p) * 2 * KX_NS + 2 * (k)))
+
+  // ---- conductivity, and per-species viscosity factors b_k = 1/w_k (to tensor memory) ----
+  {
+    real s1[P], s2[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) s1[p] = s2[p] = 0;
+#pragma unroll 1
+    for (int kb = 0; kb < KX_NB; kb++) {
+      real b[P][TB];
+#pragma unroll
+      for (int i = 0; i < TB; i++) {
+        const int k = kb * TB + i;
+        if (k < KX_N) {
+          const real* cc = kx_cond[k];
+          const real* cv = kx_visc[k];
+          const real m4 = kx_m4[k];
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            const real x = X[k * LD + p * G] * Mbar[p];
+            X[k * LD + p * G] = x;
+            const real lam = kx_quartic(cc, lnT[p]);
+            s1[p] = fma(x, lam, s1[p]);
+            s2[p] = fma(x, kx_rcp(lam), s2[p]);
+            b[p][i] = kx_rcp(kx_quartic(cv, lnT[p]) * m4);
+          }
+        } else {
+#pragma unroll
+          for (int p = 0; p < P; p++) { X[k * LD + p * G] = 0; b[p][i] = 1; }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, kb * TB), b[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++)
+      if (live[p]) kx_st_stream(conductivity + id[p], (ST)(sqrT[p] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
+  }
+  kx_tm_wait_st();
+
+  int chunk = 0;
+  auto acquire = [&]() -> const real* {
+    kx_mbar_wait(&full[chunk & (STG - 1)], (chunk / STG) & 1);
+    return buf0 + (chunk & (STG - 1)) * KX_CHUNK_MAX;
+  };
+  // hand the stage back; thread 0 then refills a stage with the chunk STG - LAG ahead: with more than two
+  // stages the stage of the PREVIOUS chunk (which the other warps have normally left already), else this one
+  constexpr int LAG = STG > 2 ? 1 : 0;
+  auto release = [&]() {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) kx_mbar_arrive(&empty[chunk & (STG - 1)]);
+    if (threadIdx.x == 0 && chunk >= LAG && chunk - LAG + STG < N_CHUNKS) {
+      const int c2 = chunk - LAG + STG, s2 = c2 & (STG - 1);
+      kx_mbar_wait(&empty[s2], (c2 / STG - 1) & 1);
+      kx_bulk_load(buf0 + s2 * KX_CHUNK_MAX, kx_chunk_src(c2), kx_chunk_bytes(c2), &full[s2]);
+    }
+    chunk++;
+  };
+
+  // ---- viscosity: Wilke with the three-matvec refactoring ----
+  //      (C1 + C2 v_k/v_j)^2 = c_kj (1 + w_k b_j)^2,  Phi_k = sum_j c_kj X_j (1 + 2 w_k b_j + w_k^2 b_j^2)
+  {
+    real vis[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) vis[p] = 0;
+#pragma unroll 1
+    for (int kb = 0; kb < KX_NB; kb++) {
+      real a0[P][TB], a1[P][TB], a2[P][TB];
+#pragma unroll
+      for (int p = 0; p < P; p++)
+#pragma unroll
+        for (int i = 0; i < TB; i++) a0[p][i] = a1[p][i] = a2[p][i] = 0;
+      const real* __restrict__ cw = acquire();
+#pragma unroll 1
+      for (int jb = 0; jb < KX_NB; jb++) {
+        unsigned raw[P][2 * TB];
+        real b[P][TB];
+#pragma unroll
+        for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, jb * TB), raw[p]);
+        kx_tm_wait_ld();
+#pragma unroll
+        for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], b[p]);
+#pragma unroll
+        for (int jj = 0; jj < TB; jj++) {
+          const int j = jb * TB + jj;
+          real x[P], xb[P], xbb[P];
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            x[p] = X[j * LD + p * G];
+            xb[p] = x[p] * b[p][jj];
+            xbb[p] = xb[p] * b[p][jj];
+          }
+#pragma unroll
+          for (int i = 0; i < TB; i++) {
+            const real c = cw[j * TB + i];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+              a0[p][i] = fma(c, x[p], a0[p][i]);
+              a1[p][i] = fma(c, xb[p], a1[p][i]);
+              a2[p][i] = fma(c, xbb[p], a2[p][i]);
+            }
+          }
+        }
+      }
+      release();
+#pragma unroll
+      for (int i = 0; i < TB; i++) {
+        const int k = kb * TB + i;
+        if (k < KX_N) {
+          const real* cv = kx_visc[k];
+          const real m4 = kx_m4[k];
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            const real v = kx_quartic(cv, lnT[p]);
+            const real w = v * m4;
+            const real phi = fma(w, fma(w, a2[p][i], a1[p][i] + a1[p][i]), a0[p][i]);
+            vis[p] = fma(X[k * LD + p * G] * (v * v), kx_rcp(phi), vis[p]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++)
+      if (live[p]) kx_st_stream(viscosity + id[p], (ST)(sqrT[p] * vis[p]));
+  }
+
+  // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj over tiles of the lower triangle; the
+  //      coefficients of a pair are fetched once for the P states ----
+#pragma unroll 1
+  for (int kb = 0; kb < KX_NB; kb++) {
+    real xk[P][TB], sk[P][TB];
+#pragma unroll
+    for (int p = 0; p < P; p++)
+#pragma unroll
+      for (int i = 0; i < TB; i++) { xk[p][i] = X[(kb * TB + i) * LD + p * G]; sk[p][i] = 0; }
+#pragma unroll 1
+    for (int jb = 0; jb < kb; jb++) {
+      real xj[P][TB], sj[P][TB];
+      unsigned raw[P][2 * TB];
+      // running sums of the column block: requested from tensor memory now, unpacked after the first tile row
+      kx_tm_wait_st();
+#pragma unroll
+      for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, jb * TB), raw[p]);
+#pragma unroll
+      for (int p = 0; p < P; p++)
+#pragma unroll
+        for (int i = 0; i < TB; i++) xj[p][i] = X[(jb * TB + i) * LD + p * G];
+      const real2* __restrict__ tile = reinterpret_cast<const real2*>(acquire());
+      kx_tm_wait_ld();
+#pragma unroll
+      for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], sj[p]);
+#pragma unroll
+      for (int i = 0; i < TB; i++) {
+        real d[P][TB];
+#pragma unroll
+        for (int j = 0; j < TB; j++) {
+          const real2* cp = tile + (i * TB + j) * 3;
+          const real2 c01 = cp[0], c23 = cp[1], c4 = cp[2];
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            const real q = fma(c4.x, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
+            d[p][j] = KX_RCP_DIFF ? q : kx_rcp(q);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+          real se = 0, so = 0;
+#pragma unroll
+          for (int j = 0; j < TB; j++) {
+            if (j & 1) so = fma(xj[p][j], d[p][j], so); else se = fma(xj[p][j], d[p][j], se);
+            sj[p][j] = fma(xk[p][i], d[p][j], sj[p][j]);
+          }
+          sk[p][i] += se + so;
+        }
+      }
+      release();
+#pragma unroll
+      for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, jb * TB), sj[p]);
+    }
+    // diagonal tile: pairs i > j inside the block
+    {
+      const real2* __restrict__ tile = reinterpret_cast<const real2*>(acquire());
+#pragma unroll
+      for (int i = 1; i < TB; i++) {
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+          const real2* cp = tile + (i * TB + j) * 3;
+          const real2 c01 = cp[0], c23 = cp[1], c4 = cp[2];
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            const real q = fma(c4.x, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
+            const real d = KX_RCP_DIFF ? q : kx_rcp(q);
+            sk[p][i] = fma(xk[p][j], d, sk[p][i]);
+            sk[p][j] = fma(xk[p][i], d, sk[p][j]);
+          }
+        }
+      }
+      release();
+    }
+    // first touch of this row block's sums (they replace b_k): later row blocks add their column contributions
+#pragma unroll
+    for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, kb * TB), sk[p]);
+  }
+  kx_tm_wait_st();
+
+  // ---- rho * D_km  (mix_transport.py:621-622 and transportProps.okl:43-47; p and Mbar cancel) ----
+#pragma unroll 1
+  for (int kb = 0; kb < KX_NB; kb++) {
+    unsigned raw[P][2 * TB];
+    real s[P][TB];
+#pragma unroll
+    for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, kb * TB), raw[p]);
+    kx_tm_wait_ld();
+#pragma unroll
+    for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], s[p]);
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      const real f = sqrT[p] * (real)(1.0 / 8.31446261815324);      // rho*T^1.5/(p*Mbar) = sqrt(T)/R
+#pragma unroll
+      for (int i = 0; i < TB; i++) {
+        const int k = kb * TB + i;
+        if (k < KX_N) {
+          const real num = fma(-kx_M[k], X[k * LD + p * G], Mbar[p]);
+          const real v = f * num * kx_rcp(s[p][i]);
+          if (live[p]) kx_st_stream(rhoD + id[p] + (size_t)k * offset, (ST)v);
+        }
+      }
+    }
+  }
+
+  // release tensor memory
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*reinterpret_cast<volatile unsigned*>(tm_base_slot))
+                 : "memory");
+  }
+  (void)pressure;
+#undef KX_TM
+}
