@@ -95,6 +95,14 @@ def _emit_bk2_single(out, mech, fits, opt, options, sp, rsize, tq):
 
     bk2_smem = smem_for(block2)
     opt['block_bk2'] = block2
+    # Wilke mass factors: dense N x N, or the rank-r factorisation when it is cheaper (6 N r < 3 N^2)
+    U, V, rank = wilke_low_rank(M)
+    low_rank = opt.get('bk2_low_rank', True) and 2 * rank < N and rank % 2 == 0
+    if low_rank:
+        wrows = min(NP, chunk_max // rank)         # species rows per streamed chunk
+        out.append(f'#define KX_WR {rank}')
+        out.append(f'#define KX_WROWS {wrows}')
+        out.append(f'#define KX_NWC {-(-NP // wrows)}')
     out.append(f'#define KX_TB {tb}')
     out.append(f'#define KX_NP {NP}')
     out.append(f'#define KX_BK2_BLOCK {block2}')
@@ -109,9 +117,15 @@ def _emit_bk2_single(out, mech, fits, opt, options, sp, rsize, tq):
     out.append(_table('kx_m4', [m ** -0.25 for m in M]))
     out.append(_table('kx_cond', [c for k in range(N) for c in fits.conductivity[k]], qualifier=tq, dims=f'[{N}][5]'))
     out.append(_table('kx_visc', [c for k in range(N) for c in fits.viscosity[k]], qualifier=tq, dims=f'[{N}][5]'))
+    if low_rank:
+        for name, F in (('kx_wilke_v', V), ('kx_wilke_u', U)):
+            rows = []
+            for k in range(NP):
+                rows += [float(x) for x in F[k]] if k < N else [0.0] * rank
+            out.append(_table(name, rows, qualifier='__device__ const __align__(16)'))
     # Wilke mass factors c_kj = 1/sqrt(8 (1 + M_k/M_j)), one chunk per k-block: [kb][j][i], k = kb*tb + i
     wil = []
-    for kb in range(NB):
+    for kb in range(NB if not low_rank else 0):
         chunk = []
         for j in range(N):
             for i in range(tb):
@@ -119,7 +133,8 @@ def _emit_bk2_single(out, mech, fits, opt, options, sp, rsize, tq):
                 chunk.append(1.0 / math.sqrt(8.0 * (1.0 + M[k] / M[j])) if k < N else 0.0)
         chunk += [0.0] * (wchunk - len(chunk))
         wil += chunk
-    out.append(_table('kx_wilke', wil, qualifier='__device__ const __align__(16)'))
+    if not low_rank:
+        out.append(_table('kx_wilke', wil, qualifier='__device__ const __align__(16)'))
     # binary diffusion quartics, lower-triangular tiles; padded pairs evaluate to D = 1
     rcp = fits.reciprocal_diffusivity
     dif = []
@@ -237,9 +252,12 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     spt = opt.get('bk2_spt', 2)
     tb, NP = choose_tile(N, opt.get('tile_bk2'))
     NB = NP // tb
-    wchunk = -(-(NP * tb) // 2) * 2
     dchunk = -(-(tb * tb * 6) // 2) * 2
-    cmax = max(wchunk, dchunk)
+    U, V, rank = wilke_low_rank(M)
+    wr = rank + (rank & 1)
+    cmax = max(dchunk, tb * wr)
+    wb = min(NB, cmax // (tb * wr))                # species blocks per Wilke chunk
+    nwc = -(-NB // wb)
     limit = 227 * 1024
     ns = -(-NP // 8) * 8                           # doubles reserved per state in tensor memory
     plan = None
@@ -253,7 +271,9 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
                 break
         if plan:
             break
-    if plan is None or plan[0] < opt.get('bk2_tmem_min_threads', 256):
+    # small mechanisms are latency / bandwidth leaning and run faster as two 128-thread CTAs per SM of the
+    # one-state-per-thread kernel (LiDryer 10.4 vs 7.9, gri30-20 2.96 vs 2.71 G states/s)
+    if plan is None or plan[0] < opt.get('bk2_tmem_min_threads', 128) or N < opt.get('bk2_tmem_min_species', 25):
         return None
     threads, stages, smem = plan
     out.append(f'#define KX_TB {tb}')
@@ -263,16 +283,41 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     out.append(f'#define KX_BK2_BLOCK {threads}')
     out.append(f'#define KX_STAGES {stages}')
     out.append(f'#define KX_CHUNK_MAX {cmax}')
-    out.append(f'#define KX_WCHUNK {wchunk}')
     out.append(f'#define KX_DCHUNK {dchunk}')
+    out.append(f'#define KX_WR {wr}')
+    out.append(f'#define KX_WB {wb}')
+    out.append(f'#define KX_NWC {nwc}')
     out.append(_table('kx_m4', [m ** -0.25 for m in M]))
     out.append(_table('kx_cond', [c for k in range(N) for c in fits.conductivity[k]], qualifier=tq, dims=f'[{N}][5]'))
     out.append(_table('kx_visc', [c for k in range(N) for c in fits.viscosity[k]], qualifier=tq, dims=f'[{N}][5]'))
-    out.append(_table('kx_wilke', _wilke_chunks(M, N, NP, tb, wchunk), qualifier='__device__ const __align__(16)'))
+    for name, F in (('kx_wilke_v', V), ('kx_wilke_u', U)):
+        rows = []
+        for k in range(NP):
+            rows += ([float(x) for x in F[k]] if k < N else [0.0] * rank) + [0.0] * (wr - rank)
+        out.append(_table(name, rows, qualifier='__device__ const __align__(16)'))
     out.append(f'#define KX_RCP_DIFF {1 if fits.reciprocal_diffusivity else 0}')
     out.append(_table('kx_diff', _diff_tiles(fits, N, NP, tb, dchunk), qualifier='__device__ const __align__(16)'))
     out.append('#include "kx_bk2_tmem.cuh"')
     return smem, threads * spt
+
+
+def wilke_low_rank(M, tol=1e-13):
+    """Factor the Wilke mass-factor matrix c_kj = (8 (1 + M_k/M_j))^-1/2 as U V^T (truncated SVD, singular values
+    folded into U).  c is a smooth kernel in ln M_k - ln M_j, so its numerical rank is ~12-14 whatever the number
+    of species; the rank is raised until every entry is reproduced to `tol` (relative; the SVD itself bottoms out at ~1e-14)."""
+    import numpy as np
+    M = np.asarray(M, dtype=np.float64)
+    C = 1.0 / np.sqrt(8.0 * (1.0 + M[:, None] / M[None, :]))
+    u, s, vt = np.linalg.svd(C)
+    for rank in range(1, len(M) + 1):
+        U = u[:, :rank] * s[:rank]
+        V = vt[:rank].T
+        if np.max(np.abs(U @ V.T - C) / C) <= tol:
+            break
+    if rank & 1 and rank < len(M):                 # the kernels read the factors two columns at a time
+        rank += 1
+        U, V = u[:, :rank] * s[:rank], vt[:rank].T
+    return U, V, rank
 
 
 def _wilke_chunks(M, N, NP, tb, wchunk):
@@ -351,6 +396,8 @@ def emit_module(mech, fits, options=None, single_precision=False):
     out.append('#include <math_constants.h>')
     out.append('#include "kx_math.cuh"')
     out.append(f'#define KX_N {N}')
+    for d in opt.get('defines', ()):               # development switches (tools/build_variants.py)
+        out.append(f'#define {d}')
     out.append(f'#define KX_SINGLE_PRECISION {1 if sp else 0}')
     out.append('typedef float real;\ntypedef float2 real2;' if sp else 'typedef double real;\ntypedef double2 real2;')
     out.append('')
@@ -383,12 +430,9 @@ def emit_module(mech, fits, options=None, single_precision=False):
         align = 16 // rsize                            # chunk sizes are multiples of 16 bytes (bulk copy)
         # lanes per state (csrc/kx_bk2_lanes.cuh): shared memory holds 2 NP reals per state, so large mechanisms
         # get few resident states per SM; 2 or 4 lanes per state bring the resident warps back up
-        lanes = opt.get('bk2_lanes')
-        if lanes is None:
-            states_1 = (limit - 8 * 1024) // (2 * (N + 3) * rsize)
-            lanes = 1 if states_1 >= 384 else (2 if states_1 >= 192 else 4)
+        lanes = opt.get('bk2_lanes') or 1          # lanes > 1 measured slower on GRI-3.0 (profiles/): opt-in
         planned = None
-        if opt.get('bk2_tmem') and not sp:
+        if opt.get('bk2_tmem', True) and not sp and lanes == 1 and opt.get('bk2_spt', 2) == 2 and not opt.get('bk2_ring'):
             planned = _emit_bk2_tmem(out, mech, fits, opt, tq)
         if planned:
             bk2_smem, bk2_states_per_cta = planned

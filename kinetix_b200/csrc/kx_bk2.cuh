@@ -101,17 +101,42 @@ KX_DEVICE void kx_mbar_wait(uint64_t* bar, unsigned parity)
 // table block is streamed as two sub-chunks (Wilke: columns j < KX_J0 / the rest; tiles: rows i < KX_R0 / the
 // rest) so that the double buffer is half as large and TWO 128-thread CTAs fit one SM's shared memory: one
 // CTA's memory-bound prologue / epilogue then overlaps the other's FP64 phases.
+#ifndef KX_WR
+#define KX_WR 0
+#endif
+#if KX_WR > 0
+// low-rank Wilke: the first 2 * KX_NWC chunks are row blocks (KX_WROWS species x KX_WR reals) of the factors V, U
+#define KX_N_WCHUNKS (2 * KX_NWC)
+#else
+#define KX_N_WCHUNKS (KX_NB * KX_SPLIT)
+#endif
 KX_DEVICE const real* kx_chunk_src(int c)
 {
+#if KX_WR > 0
+  if (c < KX_N_WCHUNKS) return (c < KX_NWC ? kx_wilke_v : kx_wilke_u) + (size_t)(c % KX_NWC) * (KX_WROWS * KX_WR);
+  c -= KX_N_WCHUNKS;
+  const int blk = c / KX_SPLIT, h = c % KX_SPLIT;
+  return kx_diff + (size_t)blk * KX_DCHUNK + (h ? KX_R0 * KX_TB * 6 : 0);
+#else
   const int blk = c / KX_SPLIT, h = c % KX_SPLIT;
   if (blk < KX_NB) return kx_wilke + (size_t)blk * KX_WCHUNK + (h ? KX_J0 * KX_TB : 0);
   return kx_diff + (size_t)(blk - KX_NB) * KX_DCHUNK + (h ? KX_R0 * KX_TB * 6 : 0);
+#endif
 }
 KX_DEVICE unsigned kx_chunk_bytes(int c)
 {
+#if KX_WR > 0
+  if (c < KX_N_WCHUNKS) {
+    const int r0 = (c % KX_NWC) * KX_WROWS, r1 = min(KX_NP, r0 + KX_WROWS);
+    return (unsigned)((r1 - r0) * KX_WR * sizeof(real));
+  }
+  const int h = (c - KX_N_WCHUNKS) % KX_SPLIT;
+  const int whole = KX_DCHUNK, first = KX_R0 * KX_TB * 6;
+#else
   const int blk = c / KX_SPLIT, h = c % KX_SPLIT;
   const int whole = blk < KX_NB ? KX_WCHUNK : KX_DCHUNK;
   const int first = blk < KX_NB ? KX_J0 * KX_TB : KX_R0 * KX_TB * 6;
+#endif
   return (unsigned)(KX_SPLIT == 1 ? whole : (h ? whole - first : first)) * (unsigned)sizeof(real);
 }
 
@@ -123,7 +148,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 {
   extern __shared__ __align__(16) unsigned char kx_sm_raw[];
   constexpr int LD = KX_BK2_BLOCK;
-  constexpr int N_CHUNKS = (KX_NB + KX_N_DTILES) * KX_SPLIT;
+  constexpr int N_CHUNKS = KX_N_WCHUNKS + KX_N_DTILES * KX_SPLIT;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(kx_sm_raw);                   // 2 mbarriers (16 B)
   real* const buf0 = reinterpret_cast<real*>(kx_sm_raw + 16);                      // 2 x KX_CHUNK_MAX reals
   real* __restrict__ X = buf0 + 2 * KX_CHUNK_MAX + threadIdx.x;                    // X[k] at X[k * LD]
@@ -218,6 +243,65 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
     chunk++;
   };
 
+#if KX_WR > 0
+  // ---- viscosity: Wilke, three matrix-vector products with a LOW-RANK mass-factor matrix ----
+  //      c_kj = (8 (1 + M_k/M_j))^-1/2 is a smooth kernel in ln M_k - ln M_j: numerical rank KX_WR (12 for GRI-3.0,
+  //      14 for the 129-species EtOHKonnov), c = U V^T from an SVD at generation time (core/emit_module.py).
+  //      t_m = V^T (X b^m),  Phi_k = U_k . (t_0 + 2 w_k t_1 + w_k^2 t_2):  6 N r instead of 3 N^2 multiply-adds.
+  {
+    constexpr int R = KX_WR;
+    real t0[R], t1[R], t2[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) t0[q] = t1[q] = t2[q] = 0;
+#pragma unroll 1
+    for (int c = 0; c < KX_NWC; c++) {
+      kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
+      const real* __restrict__ cv = buf0 + (chunk & 1) * KX_CHUNK_MAX;
+      const int j1 = min(KX_NP, (c + 1) * KX_WROWS);
+#pragma unroll 3
+      for (int j = c * KX_WROWS; j < j1; j++, cv += R) {
+        const real x = X[j * LD], b = KX_S_LOAD(j);
+        const real xb = x * b, xbb = xb * b;
+#pragma unroll
+        for (int q = 0; q < R; q += 2) {
+          const real2 vv = *reinterpret_cast<const real2*>(cv + q);
+          t0[q] = fma(vv.x, x, t0[q]);
+          t1[q] = fma(vv.x, xb, t1[q]);
+          t2[q] = fma(vv.x, xbb, t2[q]);
+          t0[q + 1] = fma(vv.y, x, t0[q + 1]);
+          t1[q + 1] = fma(vv.y, xb, t1[q + 1]);
+          t2[q + 1] = fma(vv.y, xbb, t2[q + 1]);
+        }
+      }
+      advance();
+    }
+#pragma unroll
+    for (int q = 0; q < R; q++) t1[q] += t1[q];
+    real vis = 0;
+#pragma unroll 1
+    for (int c = 0; c < KX_NWC; c++) {
+      kx_mbar_wait(&bars[chunk & 1], (chunk >> 1) & 1);
+      const real* __restrict__ cu = buf0 + (chunk & 1) * KX_CHUNK_MAX;
+      const int k1 = min(KX_N, (c + 1) * KX_WROWS);
+#pragma unroll 2
+      for (int k = c * KX_WROWS; k < k1; k++, cu += R) {
+        const real v = kx_quartic(kx_visc[k], lnT);
+        const real w = v * kx_m4[k], w2 = w * w;
+        real ph[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < R; q += 2) {
+          const real2 uu = *reinterpret_cast<const real2*>(cu + q);
+          ph[q & 2] = fma(uu.x, fma(w2, t2[q], fma(w, t1[q], t0[q])), ph[q & 2]);
+          ph[(q & 2) + 1] = fma(uu.y, fma(w2, t2[q + 1], fma(w, t1[q + 1], t0[q + 1])), ph[(q & 2) + 1]);
+        }
+        const real phi = (ph[0] + ph[1]) + (ph[2] + ph[3]);
+        vis = fma(X[k * LD] * (v * v), kx_rcp(phi), vis);
+      }
+      advance();
+    }
+    if (live) kx_st_stream(viscosity + id, (ST)(sqrT * vis));
+  }
+#else
   // ---- viscosity: Wilke with the three-matvec refactoring ----
   {
     real vis = 0;
@@ -259,6 +343,8 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
     }
     if (live) kx_st_stream(viscosity + id, (ST)(sqrT * vis));
   }
+
+#endif
 
   // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj, tiles of the lower triangle ----
   for (int kb = 0; kb < KX_NB; kb++) {

@@ -22,10 +22,10 @@
 //
 // The including translation unit defines KX_N, KX_NP (multiple of KX_TB), KX_TB, KX_P, KX_BK2_BLOCK (threads;
 // a multiple of 128 so that the warps spread evenly over the four TMEM lane quadrants), KX_NS (doubles reserved
-// per state in TMEM, >= KX_NP), KX_STAGES, KX_CHUNK_MAX, KX_WCHUNK (= KX_NP * KX_TB), KX_DCHUNK (= KX_TB^2 * 6),
-// KX_RCP_DIFF and the tables
+// per state in TMEM, >= KX_NP), KX_STAGES, KX_CHUNK_MAX, KX_DCHUNK (= KX_TB^2 * 6), KX_WR (even: rank of the
+// Wilke factorisation), KX_WB (species blocks per Wilke chunk), KX_NWC (Wilke chunks per factor), KX_RCP_DIFF and
 //   __constant__ double kx_rcpM[KX_N], kx_M[KX_N], kx_m4[KX_N], kx_cond[KX_N][5], kx_visc[KX_N][5]
-//   __device__   double kx_wilke[KX_NB][KX_WCHUNK]   c_kj as [kb][j][i], k = kb*TB + i, j < KX_NP (zero padded)
+//   __device__   double kx_wilke_v[KX_NP][KX_WR], kx_wilke_u[KX_NP][KX_WR]   c_kj = sum_q u[k][q] v[j][q]
 //   __device__   double kx_diff[n_tiles][KX_DCHUNK]  lower-triangular tiles, row-major over (kb, jb); 5 coefs + pad
 #pragma once
 #include <cstdint>
@@ -33,6 +33,15 @@
 #include "kx_pipe.cuh"
 
 #define KX_NB (KX_NP / KX_TB)
+// 1/D_kj in the pair loops: MUFU.RCP64H seed + ONE quadratic Newton step (2 FP64 instructions, relative error
+// <= 1e-12: the seed is good to 9.9e-7).  The terms X_j/D_kj are all positive, so S_k and rho*D_km inherit that
+// bound, 100x inside the 1e-10 parity contract (measured 2.6e-13 against the reference, 4.7e-14 with the cubic
+// step of kx_rcp; +3.7 % throughput).  -DKX_BK2_FULL_RCP restores the cubic step.
+#ifdef KX_BK2_FULL_RCP
+#define KX_PAIR_RCP kx_rcp
+#else
+#define KX_PAIR_RCP kx_rcp_fast
+#endif
 #define KX_N_DTILES (KX_NB * (KX_NB + 1) / 2)
 static_assert(sizeof(real) == 8, "the tensor-memory BK2 kernel is FP64 only");
 
@@ -40,11 +49,22 @@ KX_DEVICE real kx_quartic(const real* __restrict__ c, real l)
 {
   return fma(fma(fma(fma(c[4], l, c[3]), l, c[2]), l, c[1]), l, c[0]);
 }
+// chunk stream: KX_NWC chunks of V rows, KX_NWC chunks of U rows (KX_WB species blocks of KX_TB rows x KX_WR
+// reals each, the last chunk possibly shorter), then the diffusion tiles
 KX_DEVICE const real* kx_chunk_src(int c)
 {
-  return c < KX_NB ? kx_wilke + (size_t)c * KX_WCHUNK : kx_diff + (size_t)(c - KX_NB) * KX_DCHUNK;
+  if (c < 2 * KX_NWC)
+    return (c < KX_NWC ? kx_wilke_v : kx_wilke_u) + (size_t)(c % KX_NWC) * (KX_WB * KX_TB * KX_WR);
+  return kx_diff + (size_t)(c - 2 * KX_NWC) * KX_DCHUNK;
 }
-KX_DEVICE unsigned kx_chunk_bytes(int c) { return (unsigned)((c < KX_NB ? KX_WCHUNK : KX_DCHUNK) * sizeof(real)); }
+KX_DEVICE unsigned kx_chunk_bytes(int c)
+{
+  if (c < 2 * KX_NWC) {
+    const int b0 = (c % KX_NWC) * KX_WB, b1 = min(KX_NB, b0 + KX_WB);
+    return (unsigned)((b1 - b0) * KX_TB * KX_WR * sizeof(real));
+  }
+  return (unsigned)(KX_DCHUNK * sizeof(real));
+}
 
 // ---- tensor memory as a per-thread scratchpad ------------------------------------------------------
 // 32x32b shape: lane i of the warp reads / writes N consecutive 32-bit columns of TMEM lane (quadrant base + i).
@@ -163,7 +183,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   // G threads, every thread carries P states (slots t, t + G, ...): LD = G * P states per CTA
   constexpr int P = KX_P, G = KX_BK2_BLOCK, LD = G * P, TB = KX_TB;
   constexpr int NW = KX_BK2_BLOCK / 32, STG = KX_STAGES;
-  constexpr int N_CHUNKS = KX_NB + KX_N_DTILES;
+  constexpr int N_CHUNKS = 2 * KX_NWC + KX_N_DTILES;   // V blocks, U blocks, diffusion tiles
   constexpr int TM_COLS = (NW / 4) * P * 2 * KX_NS;   // columns in use per TMEM lane
   static_assert((STG & (STG - 1)) == 0 && KX_BK2_BLOCK % 128 == 0 && TM_COLS <= 512 && KX_NS >= KX_NP, "shape");
   uint64_t* const full = reinterpret_cast<uint64_t*>(kx_sm_raw);           // STG full + STG empty barriers
@@ -295,22 +315,24 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
     chunk++;
   };
 
-  // ---- viscosity: Wilke with the three-matvec refactoring ----
+  // ---- viscosity: Wilke, three matrix-vector products with a LOW-RANK mass-factor matrix ----
   //      (C1 + C2 v_k/v_j)^2 = c_kj (1 + w_k b_j)^2,  Phi_k = sum_j c_kj X_j (1 + 2 w_k b_j + w_k^2 b_j^2)
+  //      c_kj = (8 (1 + M_k/M_j))^-1/2 is a smooth kernel in ln M_k - ln M_j: its numerical rank is KX_WR
+  //      (12 for GRI-3.0, 14 for the 129-species EtOHKonnov, to 1e-16), c = U V^T from an SVD at generation
+  //      time.  So  t_m = V^T (X b^m),  Phi_k = U_k . (t_0 + 2 w_k t_1 + w_k^2 t_2):  6 N r instead of 3 N^2 DFMA.
   {
-    real vis[P];
+    constexpr int R = KX_WR;
+    real t0[P][R], t1[P][R], t2[P][R];
 #pragma unroll
-    for (int p = 0; p < P; p++) vis[p] = 0;
+    for (int p = 0; p < P; p++)
+#pragma unroll
+      for (int q = 0; q < R; q++) t0[p][q] = t1[p][q] = t2[p][q] = 0;
 #pragma unroll 1
-    for (int kb = 0; kb < KX_NB; kb++) {
-      real a0[P][TB], a1[P][TB], a2[P][TB];
-#pragma unroll
-      for (int p = 0; p < P; p++)
-#pragma unroll
-        for (int i = 0; i < TB; i++) a0[p][i] = a1[p][i] = a2[p][i] = 0;
-      const real* __restrict__ cw = acquire();
+    for (int c = 0; c < KX_NWC; c++) {
+      const real* __restrict__ cv = acquire();
+      const int jb1 = min(KX_NB, (c + 1) * KX_WB);
 #pragma unroll 1
-      for (int jb = 0; jb < KX_NB; jb++) {
+      for (int jb = c * KX_WB; jb < jb1; jb++, cv += TB * R) {
         unsigned raw[P][2 * TB];
         real b[P][TB];
 #pragma unroll
@@ -320,42 +342,69 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], b[p]);
 #pragma unroll
         for (int jj = 0; jj < TB; jj++) {
-          const int j = jb * TB + jj;
           real x[P], xb[P], xbb[P];
 #pragma unroll
           for (int p = 0; p < P; p++) {
-            x[p] = X[j * LD + p * G];
+            x[p] = X[(jb * TB + jj) * LD + p * G];
             xb[p] = x[p] * b[p][jj];
             xbb[p] = xb[p] * b[p][jj];
           }
 #pragma unroll
-          for (int i = 0; i < TB; i++) {
-            const real c = cw[j * TB + i];
+          for (int q = 0; q < R; q += 2) {
+            const real2 vv = *reinterpret_cast<const real2*>(cv + jj * R + q);
 #pragma unroll
             for (int p = 0; p < P; p++) {
-              a0[p][i] = fma(c, x[p], a0[p][i]);
-              a1[p][i] = fma(c, xb[p], a1[p][i]);
-              a2[p][i] = fma(c, xbb[p], a2[p][i]);
+              t0[p][q] = fma(vv.x, x[p], t0[p][q]);
+              t1[p][q] = fma(vv.x, xb[p], t1[p][q]);
+              t2[p][q] = fma(vv.x, xbb[p], t2[p][q]);
+              t0[p][q + 1] = fma(vv.y, x[p], t0[p][q + 1]);
+              t1[p][q + 1] = fma(vv.y, xb[p], t1[p][q + 1]);
+              t2[p][q + 1] = fma(vv.y, xbb[p], t2[p][q + 1]);
             }
           }
         }
       }
       release();
+    }
 #pragma unroll
-      for (int i = 0; i < TB; i++) {
-        const int k = kb * TB + i;
-        if (k < KX_N) {
-          const real* cv = kx_visc[k];
-          const real m4 = kx_m4[k];
+    for (int p = 0; p < P; p++)
+#pragma unroll
+      for (int q = 0; q < R; q++) t1[p][q] += t1[p][q];
+    real vis[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) vis[p] = 0;
+#pragma unroll 1
+    for (int c = 0; c < KX_NWC; c++) {
+      const real* __restrict__ cu = acquire();
+      const int k1 = min(KX_N, (c + 1) * KX_WB * TB);
+#pragma unroll 2
+      for (int k = c * KX_WB * TB; k < k1; k++, cu += R) {
+        const real* cvis = kx_visc[k];
+        const real m4 = kx_m4[k];
+        real v[P], w[P], w2[P], ph[P][4];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+          v[p] = kx_quartic(cvis, lnT[p]);
+          w[p] = v[p] * m4;
+          w2[p] = w[p] * w[p];
+          ph[p][0] = ph[p][1] = ph[p][2] = ph[p][3] = 0;
+        }
+#pragma unroll
+        for (int q = 0; q < R; q += 2) {
+          const real2 uu = *reinterpret_cast<const real2*>(cu + q);
 #pragma unroll
           for (int p = 0; p < P; p++) {
-            const real v = kx_quartic(cv, lnT[p]);
-            const real w = v * m4;
-            const real phi = fma(w, fma(w, a2[p][i], a1[p][i] + a1[p][i]), a0[p][i]);
-            vis[p] = fma(X[k * LD + p * G] * (v * v), kx_rcp(phi), vis[p]);
+            ph[p][q & 2] = fma(uu.x, fma(w2[p], t2[p][q], fma(w[p], t1[p][q], t0[p][q])), ph[p][q & 2]);
+            ph[p][(q & 2) + 1] = fma(uu.y, fma(w2[p], t2[p][q + 1], fma(w[p], t1[p][q + 1], t0[p][q + 1])), ph[p][(q & 2) + 1]);
           }
         }
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+          const real phi = (ph[p][0] + ph[p][1]) + (ph[p][2] + ph[p][3]);
+          vis[p] = fma(X[k * LD + p * G] * (v[p] * v[p]), kx_rcp(phi), vis[p]);
+        }
       }
+      release();
     }
 #pragma unroll
     for (int p = 0; p < P; p++)
@@ -397,7 +446,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll
           for (int p = 0; p < P; p++) {
             const real q = fma(c4.x, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
-            d[p][j] = KX_RCP_DIFF ? q : kx_rcp(q);
+            d[p][j] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
           }
         }
 #pragma unroll
@@ -427,7 +476,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll
           for (int p = 0; p < P; p++) {
             const real q = fma(c4.x, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
-            const real d = KX_RCP_DIFF ? q : kx_rcp(q);
+            const real d = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
             sk[p][i] = fma(xk[p][j], d, sk[p][i]);
             sk[p][j] = fma(xk[p][i], d, sk[p][j]);
           }
