@@ -23,8 +23,8 @@ ABI_VERSION = 1
 def _table(name, rows, qualifier='__constant__', dims=None, ctype='real'):
     """`real` is typedef'd per module (double, or float in the --single-precision module); literals are
     written in full double precision and rounded by the compiler."""
-    flat = [float(v) for v in rows]
-    body = ',\n  '.join(', '.join(f'(real){_lit(v)}' if ctype == 'real' else _lit(v) for v in flat[i:i + 4])
+    flat = [int(v) for v in rows] if ctype == 'int' else [float(v) for v in rows]
+    body = ',\n  '.join(', '.join(f'(real){_lit(v)}' if ctype == 'real' else (str(v) if ctype == 'int' else _lit(v)) for v in flat[i:i + 4])
                         for i in range(0, len(flat), 4))
     dims = dims or f'[{len(flat)}]'
     return f'{qualifier} {ctype} {name}{dims} = {{\n  {body}\n}};\n'
@@ -245,29 +245,39 @@ def _emit_bk2_lanes(out, mech, fits, opt, lanes, rsize, tq):
 
 
 def _emit_bk2_tmem(out, mech, fits, opt, tq):
-    """Tables + macros for csrc/kx_bk2_tmem.cuh (two states per thread, S_k in tensor memory, FP64).
-    Returns (smem bytes, states per CTA) or None when the mechanism does not fit the layout."""
+    """Tables + macros for csrc/kx_bk2_tmem.cuh (persistent CTAs, two states per thread, S_k in tensor memory,
+    FP64).  Returns (smem bytes, states per CTA round, persistent=True) or None when the mechanism does not fit."""
     N = mech.n_species
     M = mech.molar_masses
     spt = opt.get('bk2_spt', 2)
     tb, NP = choose_tile(N, opt.get('tile_bk2'))
     NB = NP // tb
-    dchunk = -(-(tb * tb * 6) // 2) * 2
     U, V, rank = wilke_low_rank(M)
     wr = rank + (rank & 1)
-    cmax = max(dchunk, tb * wr)
-    wb = min(NB, cmax // (tb * wr))                # species blocks per Wilke chunk
-    nwc = -(-NB // wb)
     limit = 227 * 1024
     ns = -(-NP // 8) * 8                           # doubles reserved per state in tensor memory
+    dchunk = tb * tb * 5
+    cmax0 = max(dchunk, tb * (wr + 6))             # at least one species block per Wilke / species chunk
+
+    def rows(width):
+        return tb * min(NB, max(1, cmax0 // (tb * width)))
+    srows, vrows, urows = rows(12), rows(wr), rows(wr + 6)
+    cmax = -(-max(dchunk, srows * 12, vrows * wr, urows * (wr + 6)) // 2) * 2
     plan = None
     for threads in (256, 128):
         if (threads // 128) * spt * 2 * ns > 512:  # columns per TMEM lane
             continue
-        for stages in ((opt['bk2_stages'],) if opt.get('bk2_stages') else (4, 2)):
-            smem = 16 * stages + 16 + (stages * cmax + NP * threads * spt) * 8
-            if smem <= limit:
-                plan = (threads, stages, smem)
+        # two half-CTA teams with skewed phases were measured SLOWER (549 vs 608 M states/s on GRI-3.0): the teams
+        # run different parts of the ~120 KB unrolled body and miss the instruction cache (no_instruction stalls
+        # 4 % -> 18 %, profiles/ncu_r01_bk2_teams.txt); kept as an option
+        teams_opts = (opt['bk2_teams'],) if opt.get('bk2_teams') else (1,)
+        for teams in teams_opts:
+            for stages in ((opt['bk2_stages'],) if opt.get('bk2_stages') else (4, 2)):
+                smem = 16 * stages * teams + 16 + (teams * stages * cmax + N * threads * spt) * 8
+                if smem <= limit:
+                    plan = (threads, teams, stages, smem)
+                    break
+            if plan:
                 break
         if plan:
             break
@@ -275,30 +285,62 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     # one-state-per-thread kernel (LiDryer 10.4 vs 7.9, gri30-20 2.96 vs 2.71 G states/s)
     if plan is None or plan[0] < opt.get('bk2_tmem_min_threads', 128) or N < opt.get('bk2_tmem_min_species', 25):
         return None
-    threads, stages, smem = plan
+    threads, teams, stages, smem = plan
+
+    # the coefficient stream of one batch, chunk by chunk (each chunk padded to a 16-byte multiple)
+    stream, offs = [], [0]
+
+    def add_chunk(vals):
+        vals = list(vals)
+        vals += [0.0] * (len(vals) & 1)
+        assert len(vals) <= cmax
+        stream.extend(vals)
+        offs.append(len(stream))
+
+    def species_row(k):
+        if k < N:
+            return list(fits.conductivity[k]) + list(fits.viscosity[k]) + [M[k] ** -0.25, 0.0]
+        return [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0.0]
+    for r0 in range(0, NP, srows):
+        add_chunk(v for k in range(r0, min(NP, r0 + srows)) for v in species_row(k))
+    for r0 in range(0, NP, vrows):
+        add_chunk(v for k in range(r0, min(NP, r0 + vrows))
+                  for v in (([float(x) for x in V[k]] if k < N else [0.0] * rank) + [0.0] * (wr - rank)))
+    for r0 in range(0, NP, urows):
+        add_chunk(v for k in range(r0, min(NP, r0 + urows))
+                  for v in (([float(x) for x in U[k]] + [0.0] * (wr - rank) + list(fits.viscosity[k]) + [M[k] ** -0.25])
+                            if k < N else [0.0] * wr + [1.0, 0, 0, 0, 0, 1.0]))
+    nsc, nvc, nuc = -(-NP // srows), -(-NP // vrows), -(-NP // urows)
+    for kb in range(NB):
+        for jb in range(kb + 1):
+            tile = []
+            for i in range(tb):
+                for j in range(tb):
+                    k, jj = kb * tb + i, jb * tb + j
+                    tile += list(fits.diffusivity[k][jj]) if (k < N and jj < N and k > jj) else [1.0, 0.0, 0.0, 0.0, 0.0]
+            add_chunk(tile)
+    n_chunks = len(offs) - 1
     out.append(f'#define KX_TB {tb}')
     out.append(f'#define KX_NP {NP}')
     out.append(f'#define KX_P {spt}')
+    out.append(f'#define KX_TEAMS {teams}')
     out.append(f'#define KX_NS {ns}')
     out.append(f'#define KX_BK2_BLOCK {threads}')
     out.append(f'#define KX_STAGES {stages}')
     out.append(f'#define KX_CHUNK_MAX {cmax}')
-    out.append(f'#define KX_DCHUNK {dchunk}')
     out.append(f'#define KX_WR {wr}')
-    out.append(f'#define KX_WB {wb}')
-    out.append(f'#define KX_NWC {nwc}')
-    out.append(_table('kx_m4', [m ** -0.25 for m in M]))
-    out.append(_table('kx_cond', [c for k in range(N) for c in fits.conductivity[k]], qualifier=tq, dims=f'[{N}][5]'))
-    out.append(_table('kx_visc', [c for k in range(N) for c in fits.viscosity[k]], qualifier=tq, dims=f'[{N}][5]'))
-    for name, F in (('kx_wilke_v', V), ('kx_wilke_u', U)):
-        rows = []
-        for k in range(NP):
-            rows += ([float(x) for x in F[k]] if k < N else [0.0] * rank) + [0.0] * (wr - rank)
-        out.append(_table(name, rows, qualifier='__device__ const __align__(16)'))
+    out.append(f'#define KX_SROWS {srows}')
+    out.append(f'#define KX_VROWS {vrows}')
+    out.append(f'#define KX_UROWS {urows}')
+    out.append(f'#define KX_NSC {nsc}')
+    out.append(f'#define KX_NVC {nvc}')
+    out.append(f'#define KX_NUC {nuc}')
+    out.append(f'#define KX_N_CHUNKS {n_chunks}')
     out.append(f'#define KX_RCP_DIFF {1 if fits.reciprocal_diffusivity else 0}')
-    out.append(_table('kx_diff', _diff_tiles(fits, N, NP, tb, dchunk), qualifier='__device__ const __align__(16)'))
+    out.append(_table('kx_chunk_off', offs, qualifier='__constant__', ctype='int'))
+    out.append(_table('kx_bk2_stream', stream, qualifier='__device__ const __align__(16)'))
     out.append('#include "kx_bk2_tmem.cuh"')
-    return smem, threads * spt
+    return smem, threads * spt, True
 
 
 def wilke_low_rank(M, tol=1e-13):
@@ -434,8 +476,9 @@ def emit_module(mech, fits, options=None, single_precision=False):
         planned = None
         if opt.get('bk2_tmem', True) and not sp and lanes == 1 and opt.get('bk2_spt', 2) == 2 and not opt.get('bk2_ring'):
             planned = _emit_bk2_tmem(out, mech, fits, opt, tq)
+        bk2_persistent = False
         if planned:
-            bk2_smem, bk2_states_per_cta = planned
+            bk2_smem, bk2_states_per_cta, bk2_persistent = planned
         elif lanes > 1 or opt.get('bk2_spt', 1) > 1 or opt.get('bk2_ring'):
             bk2_smem, bk2_states_per_cta = _emit_bk2_lanes(out, mech, fits, opt, lanes, rsize, tq)
         else:
@@ -508,6 +551,15 @@ static int launch_thermo(long long n, long long offsetT, long long offset, doubl
 }}
 ''')
     if has_bk2:
+        persistent_grid = '''  {   // persistent CTAs: one per SM, each loops over batches of per_cta states
+    static int n_sm = 0;
+    if (!n_sm) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1002;
+    }
+    if (grid > (unsigned)n_sm) grid = (unsigned)n_sm;
+  }
+''' if bk2_persistent else ''
         out.append(f'''
 template <typename S>
 static int launch_bk2(long long n, long long offsetT, long long offset, double pressure, const void* state,
@@ -519,8 +571,8 @@ static int launch_bk2(long long n, long long offsetT, long long offset, double p
     if (int e = kxm_set_smem(kx_bk2<S>, smem)) return e;
     configured = true;
   }}
-  const unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
-  kx_bk2<S><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
+  unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
+{persistent_grid}  kx_bk2<S><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
                                            (S*)viscosity, (S*)rhoD, Tref);
   return (int)cudaGetLastError();
 }}

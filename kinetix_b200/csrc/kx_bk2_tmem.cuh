@@ -49,22 +49,15 @@ KX_DEVICE real kx_quartic(const real* __restrict__ c, real l)
 {
   return fma(fma(fma(fma(c[4], l, c[3]), l, c[2]), l, c[1]), l, c[0]);
 }
-// chunk stream: KX_NWC chunks of V rows, KX_NWC chunks of U rows (KX_WB species blocks of KX_TB rows x KX_WR
-// reals each, the last chunk possibly shorter), then the diffusion tiles
-KX_DEVICE const real* kx_chunk_src(int c)
-{
-  if (c < 2 * KX_NWC)
-    return (c < KX_NWC ? kx_wilke_v : kx_wilke_u) + (size_t)(c % KX_NWC) * (KX_WB * KX_TB * KX_WR);
-  return kx_diff + (size_t)(c - 2 * KX_NWC) * KX_DCHUNK;
-}
-KX_DEVICE unsigned kx_chunk_bytes(int c)
-{
-  if (c < 2 * KX_NWC) {
-    const int b0 = (c % KX_NWC) * KX_WB, b1 = min(KX_NB, b0 + KX_WB);
-    return (unsigned)((b1 - b0) * KX_TB * KX_WR * sizeof(real));
-  }
-  return (unsigned)(KX_DCHUNK * sizeof(real));
-}
+// The coefficient stream of one batch: KX_N_CHUNKS chunks of the concatenated table kx_bk2_stream, chunk c =
+// reals [kx_chunk_off[c], kx_chunk_off[c + 1]):
+//   KX_NSC chunks of the species table  (KX_SROWS rows x 12: conductivity quartic, viscosity quartic, M^-1/4, -)
+//   KX_NVC chunks of the Wilke factor V (KX_VROWS rows x KX_WR)
+//   KX_NUC chunks of the Wilke factor U (KX_UROWS rows x (KX_WR + 6): U row, viscosity quartic, M^-1/4)
+//   the lower-triangular diffusion tiles (KX_TB^2 pairs x 5 coefficients), row-major over (kb, jb <= kb)
+// Rows per chunk are multiples of KX_TB; padded species rows hold quartics = 1, M^-1/4 = 1, U = V = 0.
+KX_DEVICE const real* kx_chunk_src(int c) { return kx_bk2_stream + kx_chunk_off[c]; }
+KX_DEVICE unsigned kx_chunk_bytes(int c) { return (unsigned)((kx_chunk_off[c + 1] - kx_chunk_off[c]) * sizeof(real)); }
 
 // ---- tensor memory as a per-thread scratchpad ------------------------------------------------------
 // 32x32b shape: lane i of the warp reads / writes N consecutive 32-bit columns of TMEM lane (quadrant base + i).
@@ -180,18 +173,34 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
        ST* __restrict__ rhoD, const double Tref)
 {
   extern __shared__ __align__(16) unsigned char kx_sm_raw[];
-  // G threads, every thread carries P states (slots t, t + G, ...): LD = G * P states per CTA
-  constexpr int P = KX_P, G = KX_BK2_BLOCK, LD = G * P, TB = KX_TB;
-  constexpr int NW = KX_BK2_BLOCK / 32, STG = KX_STAGES;
-  constexpr int N_CHUNKS = 2 * KX_NWC + KX_N_DTILES;   // V blocks, U blocks, diffusion tiles
-  constexpr int TM_COLS = (NW / 4) * P * 2 * KX_NS;   // columns in use per TMEM lane
-  static_assert((STG & (STG - 1)) == 0 && KX_BK2_BLOCK % 128 == 0 && TM_COLS <= 512 && KX_NS >= KX_NP, "shape");
-  uint64_t* const full = reinterpret_cast<uint64_t*>(kx_sm_raw);           // STG full + STG empty barriers
+  // PERSISTENT CTA of TEAMS independent teams of TT threads; a thread carries P states of its team's current
+  // batch (slots t, t + TT, ...): LDT = TT * P states per batch.  Each team has its own ring of table stages,
+  // so with two teams one team's memory-bound prologue / epilogue overlaps the other's FP64 loops (the second
+  // team starts half a batch late and the offset persists).
+  constexpr int P = KX_P, TEAMS = KX_TEAMS, TT = KX_BK2_BLOCK / TEAMS, LDT = TT * P, TB = KX_TB;
+  constexpr int NWT = TT / 32, STG = KX_STAGES, R = KX_WR, RU = KX_WR + 6;
+  constexpr int N_CHUNKS = KX_N_CHUNKS;
+  constexpr int C_V = KX_NSC, C_U = C_V + KX_NVC, C_D = C_U + KX_NUC;   // first chunk of V, U, the tiles
+  constexpr int TM_COLS = (KX_BK2_BLOCK / 128) * P * 2 * KX_NS;         // columns in use per TMEM lane
+  static_assert((STG & (STG - 1)) == 0 && TT % 128 == 0 && TM_COLS <= 512 && KX_NS >= KX_NP, "shape");
+  static_assert(C_D + KX_N_DTILES == N_CHUNKS, "chunk table");
+  const int team = threadIdx.x / TT, tt = threadIdx.x % TT, warp = threadIdx.x >> 5;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(kx_sm_raw);          // per team: STG full + STG empty
+  uint64_t* const full = bars + team * 2 * STG;
   uint64_t* const empty = full + STG;
-  unsigned* const tm_base_slot = reinterpret_cast<unsigned*>(empty + STG);  // TMEM base address (16 bytes reserved)
-  real* const buf0 = reinterpret_cast<real*>(kx_sm_raw + 16 * STG + 16);   // STG x KX_CHUNK_MAX reals
-  real* __restrict__ X = buf0 + STG * KX_CHUNK_MAX + threadIdx.x;          // X[k] of state p at X[k * LD + p * G]
-  const int warp = threadIdx.x >> 5;
+  uint64_t* const skew = bars + TEAMS * 2 * STG;                          // one-time start signal for team 1
+  unsigned* const tm_base_slot = reinterpret_cast<unsigned*>(skew + 1);
+  real* const bufs = reinterpret_cast<real*>(kx_sm_raw + 16 * STG * TEAMS + 16);
+  real* const buf0 = bufs + team * STG * KX_CHUNK_MAX;                    // this team's STG stages
+  // X[k] of state p at X[k * LDT + p * TT]; only the KX_N real species have a row
+  real* __restrict__ X = bufs + TEAMS * STG * KX_CHUNK_MAX + team * (KX_N * LDT) + tt;
+  auto x_row = [&](int k) { return (k < KX_N ? k : KX_N - 1) * LDT; };
+
+  // batches of this team: b = blockIdx.x * TEAMS + team, + gridDim.x * TEAMS, ...
+  const long long n_batches = (n_states + LDT - 1) / LDT;
+  const long long b_first = (long long)blockIdx.x * TEAMS + team, b_step = (long long)gridDim.x * TEAMS;
+  const long long my_batches = b_first < n_batches ? (n_batches - b_first + b_step - 1) / b_step : 0;
+  const long long total_chunks = my_batches * N_CHUNKS;
 
   if (warp == 0) {
     // all 512 columns: this CTA is alone on its SM (shared memory), nobody else needs tensor memory
@@ -201,315 +210,329 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   }
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < STG; s++) { kx_mbar_init(&full[s], 1); kx_mbar_init(&empty[s], NW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-    for (int s = 0; s < STG; s++)
-      if (s < N_CHUNKS) kx_bulk_load(buf0 + s * KX_CHUNK_MAX, kx_chunk_src(s), kx_chunk_bytes(s), &full[s]);
-  }
-
-  bool live[P];
-  long long id[P];
-  real lnT[P], lnT2[P], lnT4[P], sqrT[P], Mbar[P];
-#pragma unroll
-  for (int p = 0; p < P; p++) {
-    const long long gid = (long long)blockIdx.x * LD + p * G + threadIdx.x;
-    live[p] = gid < n_states;
-    id[p] = live[p] ? gid : n_states - 1;   // tail slots recompute the last state, store nothing
-  }
-
-  // ---- mole fractions (transportProps.okl:23-35): batches of 32 independent row loads per state ----
-#pragma unroll
-  for (int p = 0; p < P; p++) {
-    const ST* sp = state + id[p] + offsetT;
-    const ST t_raw = kx_ld_stream(state + id[p]);
-    real acc = 0;
-    constexpr int LB = 32;
-#pragma unroll
-    for (int k0 = 0; k0 < KX_N; k0 += LB) {
-      ST y[LB];
-#pragma unroll
-      for (int i = 0; i < LB; i++)
-        if (k0 + i < KX_N) y[i] = kx_ld_stream(sp + (size_t)(k0 + i) * offset);
-#pragma unroll
-      for (int i = 0; i < LB; i++) {
-        if (k0 + i < KX_N) {
-          const real yi = (real)y[i];
-          const real w = (yi > (real)0 ? yi : (real)0) * kx_rcpM[k0 + i];
-          X[(k0 + i) * LD + p * G] = w;
-          acc += w;
-        }
-      }
+    for (int s = 0; s < TEAMS * STG; s++) {
+      kx_mbar_init(&bars[(s / STG) * 2 * STG + s % STG], 1);
+      kx_mbar_init(&bars[(s / STG) * 2 * STG + STG + s % STG], NWT);
     }
-    Mbar[p] = kx_rcp(acc);
-    const double Td = Tref * (double)t_raw;
-    lnT[p] = (real)kx_log(Td);
-    sqrT[p] = kx_sqrt((real)Td);
-    lnT2[p] = lnT[p] * lnT[p];
-    lnT4[p] = lnT2[p] * lnT2[p];
+    kx_mbar_init(skew, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-
-  // TMEM base address: visible after the allocating warp's write + CTA barrier
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();   // also: mbarrier inits visible to all threads before the first wait
+  __syncthreads();   // mbarrier inits + TMEM base address visible
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // this thread's S_k of state p: lane quadrant (warp % 4), column (2 KX_NS) ((warp / 4) P + p) + 2 k
   const unsigned tm0 = *reinterpret_cast<volatile unsigned*>(tm_base_slot) + ((unsigned)(warp & 3) << 21) +
                        (unsigned)((warp >> 2) * P * 2 * KX_NS);
 #define KX_TM(p, k) (tm0 + (unsigned)((p) * 2 * KX_NS + 2 * (k)))
 
-  // ---- conductivity, and per-species viscosity factors b_k = 1/w_k (to tensor memory) ----
-  {
-    real s1[P], s2[P];
+  if (tt == 0) {
 #pragma unroll
-    for (int p = 0; p < P; p++) s1[p] = s2[p] = 0;
-#pragma unroll 1
-    for (int kb = 0; kb < KX_NB; kb++) {
-      real b[P][TB];
-#pragma unroll
-      for (int i = 0; i < TB; i++) {
-        const int k = kb * TB + i;
-        if (k < KX_N) {
-          const real* cc = kx_cond[k];
-          const real* cv = kx_visc[k];
-          const real m4 = kx_m4[k];
-#pragma unroll
-          for (int p = 0; p < P; p++) {
-            const real x = X[k * LD + p * G] * Mbar[p];
-            X[k * LD + p * G] = x;
-            const real lam = kx_quartic(cc, lnT[p]);
-            s1[p] = fma(x, lam, s1[p]);
-            s2[p] = fma(x, kx_rcp(lam), s2[p]);
-            b[p][i] = kx_rcp(kx_quartic(cv, lnT[p]) * m4);
-          }
-        } else {
-#pragma unroll
-          for (int p = 0; p < P; p++) { X[k * LD + p * G] = 0; b[p][i] = 1; }
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, kb * TB), b[p]);
-    }
-#pragma unroll
-    for (int p = 0; p < P; p++)
-      if (live[p]) kx_st_stream(conductivity + id[p], (ST)(sqrT[p] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
+    for (int s = 0; s < STG; s++)
+      if (s < total_chunks) kx_bulk_load(buf0 + s * KX_CHUNK_MAX, kx_chunk_src(s % N_CHUNKS), kx_chunk_bytes(s % N_CHUNKS), &full[s]);
+    if (TEAMS > 1 && team == 0 && my_batches == 0) kx_mbar_arrive(skew);
   }
-  kx_tm_wait_st();
+  if (TEAMS > 1 && team == 1 && my_batches > 0) kx_mbar_wait(skew, 0);
 
-  int chunk = 0;
+  long long g = 0;   // chunks consumed so far by this team (all batches)
   auto acquire = [&]() -> const real* {
-    kx_mbar_wait(&full[chunk & (STG - 1)], (chunk / STG) & 1);
-    return buf0 + (chunk & (STG - 1)) * KX_CHUNK_MAX;
+    kx_mbar_wait(&full[g & (STG - 1)], (unsigned)(g / STG) & 1);
+    return buf0 + (g & (STG - 1)) * KX_CHUNK_MAX;
   };
-  // hand the stage back; thread 0 then refills a stage with the chunk STG - LAG ahead: with more than two
-  // stages the stage of the PREVIOUS chunk (which the other warps have normally left already), else this one
-  constexpr int LAG = STG > 2 ? 1 : 0;
+  // hand the stage back; the team's first thread refills it with the chunk STG ahead (possibly of the next batch)
   auto release = [&]() {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) kx_mbar_arrive(&empty[chunk & (STG - 1)]);
-    if (threadIdx.x == 0 && chunk >= LAG && chunk - LAG + STG < N_CHUNKS) {
-      const int c2 = chunk - LAG + STG, s2 = c2 & (STG - 1);
-      kx_mbar_wait(&empty[s2], (c2 / STG - 1) & 1);
-      kx_bulk_load(buf0 + s2 * KX_CHUNK_MAX, kx_chunk_src(c2), kx_chunk_bytes(c2), &full[s2]);
+    if ((threadIdx.x & 31) == 0) kx_mbar_arrive(&empty[g & (STG - 1)]);
+    if (tt == 0) {
+      if (g + STG < total_chunks) {
+        const int s2 = (int)(g & (STG - 1)), c2 = (int)((g + STG) % N_CHUNKS);
+        kx_mbar_wait(&empty[s2], (unsigned)(g / STG) & 1);
+        kx_bulk_load(buf0 + s2 * KX_CHUNK_MAX, kx_chunk_src(c2), kx_chunk_bytes(c2), &full[s2]);
+      }
+      if (TEAMS > 1 && team == 0 && g == N_CHUNKS / 2) kx_mbar_arrive(skew);   // lets team 1 start, half a batch late
     }
-    chunk++;
+    g++;
   };
 
-  // ---- viscosity: Wilke, three matrix-vector products with a LOW-RANK mass-factor matrix ----
-  //      (C1 + C2 v_k/v_j)^2 = c_kj (1 + w_k b_j)^2,  Phi_k = sum_j c_kj X_j (1 + 2 w_k b_j + w_k^2 b_j^2)
-  //      c_kj = (8 (1 + M_k/M_j))^-1/2 is a smooth kernel in ln M_k - ln M_j: its numerical rank is KX_WR
-  //      (12 for GRI-3.0, 14 for the 129-species EtOHKonnov, to 1e-16), c = U V^T from an SVD at generation
-  //      time.  So  t_m = V^T (X b^m),  Phi_k = U_k . (t_0 + 2 w_k t_1 + w_k^2 t_2):  6 N r instead of 3 N^2 DFMA.
-  {
-    constexpr int R = KX_WR;
-    real t0[P][R], t1[P][R], t2[P][R];
-#pragma unroll
-    for (int p = 0; p < P; p++)
-#pragma unroll
-      for (int q = 0; q < R; q++) t0[p][q] = t1[p][q] = t2[p][q] = 0;
 #pragma unroll 1
-    for (int c = 0; c < KX_NWC; c++) {
-      const real* __restrict__ cv = acquire();
-      const int jb1 = min(KX_NB, (c + 1) * KX_WB);
-#pragma unroll 1
-      for (int jb = c * KX_WB; jb < jb1; jb++, cv += TB * R) {
-        unsigned raw[P][2 * TB];
-        real b[P][TB];
+  for (long long batch = b_first; batch < n_batches; batch += b_step) {
+    bool live[P];
+    long long id[P];
+    real lnT[P], lnT2[P], lnT4[P], sqrT[P], Mbar[P];
 #pragma unroll
-        for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, jb * TB), raw[p]);
-        kx_tm_wait_ld();
+    for (int p = 0; p < P; p++) {
+      const long long gid = batch * LDT + p * TT + tt;
+      live[p] = gid < n_states;
+      id[p] = live[p] ? gid : n_states - 1;   // tail slots recompute the last state, store nothing
+    }
+
+    // ---- mole fractions (transportProps.okl:23-35): batches of 32 independent row loads per state ----
 #pragma unroll
-        for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], b[p]);
+    for (int p = 0; p < P; p++) {
+      const ST* sp = state + id[p] + offsetT;
+      const ST t_raw = kx_ld_stream(state + id[p]);
+      real acc = 0;
+      constexpr int LB = 32;
 #pragma unroll
-        for (int jj = 0; jj < TB; jj++) {
-          real x[P], xb[P], xbb[P];
+      for (int k0 = 0; k0 < KX_N; k0 += LB) {
+        ST y[LB];
 #pragma unroll
-          for (int p = 0; p < P; p++) {
-            x[p] = X[(jb * TB + jj) * LD + p * G];
-            xb[p] = x[p] * b[p][jj];
-            xbb[p] = xb[p] * b[p][jj];
+        for (int i = 0; i < LB; i++)
+          if (k0 + i < KX_N) y[i] = kx_ld_stream(sp + (size_t)(k0 + i) * offset);
+#pragma unroll
+        for (int i = 0; i < LB; i++) {
+          if (k0 + i < KX_N) {
+            const real yi = (real)y[i];
+            const real w = (yi > (real)0 ? yi : (real)0) * kx_rcpM[k0 + i];
+            X[(k0 + i) * LDT + p * TT] = w;
+            acc += w;
           }
+        }
+      }
+      Mbar[p] = kx_rcp(acc);
+      const double Td = Tref * (double)t_raw;
+      lnT[p] = (real)kx_log(Td);
+      sqrT[p] = kx_sqrt((real)Td);
+      lnT2[p] = lnT[p] * lnT[p];
+      lnT4[p] = lnT2[p] * lnT2[p];
+    }
+
+    // ---- conductivity, and per-species viscosity factors b_k = 1/w_k (to tensor memory) ----
+    {
+      real s1[P], s2[P];
 #pragma unroll
-          for (int q = 0; q < R; q += 2) {
-            const real2 vv = *reinterpret_cast<const real2*>(cv + jj * R + q);
+      for (int p = 0; p < P; p++) s1[p] = s2[p] = 0;
+#pragma unroll 1
+      for (int c = 0; c < KX_NSC; c++) {
+        const real* __restrict__ sr = acquire();
+        const int kb1 = min(KX_NB, (c + 1) * (KX_SROWS / TB));
+#pragma unroll 1
+        for (int kb = c * (KX_SROWS / TB); kb < kb1; kb++, sr += TB * 12) {
+          real b[P][TB];
+#pragma unroll
+          for (int i = 0; i < TB; i++) {
+            const int k = kb * TB + i;
+            const real* row = sr + i * 12;
+            const real m4 = row[10];
 #pragma unroll
             for (int p = 0; p < P; p++) {
-              t0[p][q] = fma(vv.x, x[p], t0[p][q]);
-              t1[p][q] = fma(vv.x, xb[p], t1[p][q]);
-              t2[p][q] = fma(vv.x, xbb[p], t2[p][q]);
-              t0[p][q + 1] = fma(vv.y, x[p], t0[p][q + 1]);
-              t1[p][q + 1] = fma(vv.y, xb[p], t1[p][q + 1]);
-              t2[p][q + 1] = fma(vv.y, xbb[p], t2[p][q + 1]);
+              const real x = k < KX_N ? X[x_row(k) + p * TT] * Mbar[p] : (real)0;
+              if (k < KX_N) X[x_row(k) + p * TT] = x;
+              const real lam = kx_quartic(row, lnT[p]);
+              s1[p] = fma(x, lam, s1[p]);
+              s2[p] = fma(x, kx_rcp(lam), s2[p]);
+              b[p][i] = kx_rcp(kx_quartic(row + 5, lnT[p]) * m4);
             }
           }
+#pragma unroll
+          for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, kb * TB), b[p]);
         }
+        release();
       }
-      release();
+#pragma unroll
+      for (int p = 0; p < P; p++)
+        if (live[p]) kx_st_stream(conductivity + id[p], (ST)(sqrT[p] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
     }
-#pragma unroll
-    for (int p = 0; p < P; p++)
-#pragma unroll
-      for (int q = 0; q < R; q++) t1[p][q] += t1[p][q];
-    real vis[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) vis[p] = 0;
-#pragma unroll 1
-    for (int c = 0; c < KX_NWC; c++) {
-      const real* __restrict__ cu = acquire();
-      const int k1 = min(KX_N, (c + 1) * KX_WB * TB);
-#pragma unroll 2
-      for (int k = c * KX_WB * TB; k < k1; k++, cu += R) {
-        const real* cvis = kx_visc[k];
-        const real m4 = kx_m4[k];
-        real v[P], w[P], w2[P], ph[P][4];
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-          v[p] = kx_quartic(cvis, lnT[p]);
-          w[p] = v[p] * m4;
-          w2[p] = w[p] * w[p];
-          ph[p][0] = ph[p][1] = ph[p][2] = ph[p][3] = 0;
-        }
-#pragma unroll
-        for (int q = 0; q < R; q += 2) {
-          const real2 uu = *reinterpret_cast<const real2*>(cu + q);
-#pragma unroll
-          for (int p = 0; p < P; p++) {
-            ph[p][q & 2] = fma(uu.x, fma(w2[p], t2[p][q], fma(w[p], t1[p][q], t0[p][q])), ph[p][q & 2]);
-            ph[p][(q & 2) + 1] = fma(uu.y, fma(w2[p], t2[p][q + 1], fma(w[p], t1[p][q + 1], t0[p][q + 1])), ph[p][(q & 2) + 1]);
-          }
-        }
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-          const real phi = (ph[p][0] + ph[p][1]) + (ph[p][2] + ph[p][3]);
-          vis[p] = fma(X[k * LD + p * G] * (v[p] * v[p]), kx_rcp(phi), vis[p]);
-        }
-      }
-      release();
-    }
-#pragma unroll
-    for (int p = 0; p < P; p++)
-      if (live[p]) kx_st_stream(viscosity + id[p], (ST)(sqrT[p] * vis[p]));
-  }
+    kx_tm_wait_st();
 
-  // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj over tiles of the lower triangle; the
-  //      coefficients of a pair are fetched once for the P states ----
-#pragma unroll 1
-  for (int kb = 0; kb < KX_NB; kb++) {
-    real xk[P][TB], sk[P][TB];
-#pragma unroll
-    for (int p = 0; p < P; p++)
-#pragma unroll
-      for (int i = 0; i < TB; i++) { xk[p][i] = X[(kb * TB + i) * LD + p * G]; sk[p][i] = 0; }
-#pragma unroll 1
-    for (int jb = 0; jb < kb; jb++) {
-      real xj[P][TB], sj[P][TB];
-      unsigned raw[P][2 * TB];
-      // running sums of the column block: requested from tensor memory now, unpacked after the first tile row
-      kx_tm_wait_st();
-#pragma unroll
-      for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, jb * TB), raw[p]);
+    // ---- viscosity: Wilke, three matrix-vector products with a LOW-RANK mass-factor matrix ----
+    //      (C1 + C2 v_k/v_j)^2 = c_kj (1 + w_k b_j)^2,  Phi_k = sum_j c_kj X_j (1 + 2 w_k b_j + w_k^2 b_j^2)
+    //      c_kj = (8 (1 + M_k/M_j))^-1/2 is a smooth kernel in ln M_k - ln M_j: its numerical rank is KX_WR
+    //      (12 for GRI-3.0, 14 for the 129-species EtOHKonnov), c = U V^T from an SVD at generation time.
+    //      So  t_m = V^T (X b^m),  Phi_k = U_k . (t_0 + 2 w_k t_1 + w_k^2 t_2):  6 N r instead of 3 N^2 DFMA.
+    {
+      real t0[P][R], t1[P][R], t2[P][R];
 #pragma unroll
       for (int p = 0; p < P; p++)
 #pragma unroll
-        for (int i = 0; i < TB; i++) xj[p][i] = X[(jb * TB + i) * LD + p * G];
-      const real2* __restrict__ tile = reinterpret_cast<const real2*>(acquire());
-      kx_tm_wait_ld();
+        for (int q = 0; q < R; q++) t0[p][q] = t1[p][q] = t2[p][q] = 0;
+#pragma unroll 1
+      for (int c = 0; c < KX_NVC; c++) {
+        const real* __restrict__ cv = acquire();
+        const int jb1 = min(KX_NB, (c + 1) * (KX_VROWS / TB));
+#pragma unroll 1
+        for (int jb = c * (KX_VROWS / TB); jb < jb1; jb++, cv += TB * R) {
+          unsigned raw[P][2 * TB];
+          real b[P][TB];
 #pragma unroll
-      for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], sj[p]);
+          for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, jb * TB), raw[p]);
+          kx_tm_wait_ld();
 #pragma unroll
-      for (int i = 0; i < TB; i++) {
-        real d[P][TB];
+          for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], b[p]);
 #pragma unroll
-        for (int j = 0; j < TB; j++) {
-          const real2* cp = tile + (i * TB + j) * 3;
-          const real2 c01 = cp[0], c23 = cp[1], c4 = cp[2];
+          for (int jj = 0; jj < TB; jj++) {
+            const int j = jb * TB + jj;
+            real x[P], xb[P], xbb[P];
 #pragma unroll
-          for (int p = 0; p < P; p++) {
-            const real q = fma(c4.x, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
-            d[p][j] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
+            for (int p = 0; p < P; p++) {
+              x[p] = j < KX_N ? X[x_row(j) + p * TT] : (real)0;
+              xb[p] = x[p] * b[p][jj];
+              xbb[p] = xb[p] * b[p][jj];
+            }
+#pragma unroll
+            for (int q = 0; q < R; q += 2) {
+              const real2 vv = *reinterpret_cast<const real2*>(cv + jj * R + q);
+#pragma unroll
+              for (int p = 0; p < P; p++) {
+                t0[p][q] = fma(vv.x, x[p], t0[p][q]);
+                t1[p][q] = fma(vv.x, xb[p], t1[p][q]);
+                t2[p][q] = fma(vv.x, xbb[p], t2[p][q]);
+                t0[p][q + 1] = fma(vv.y, x[p], t0[p][q + 1]);
+                t1[p][q + 1] = fma(vv.y, xb[p], t1[p][q + 1]);
+                t2[p][q + 1] = fma(vv.y, xbb[p], t2[p][q + 1]);
+              }
+            }
           }
         }
+        release();
+      }
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-          real se = 0, so = 0;
+      for (int p = 0; p < P; p++)
+#pragma unroll
+        for (int q = 0; q < R; q++) t1[p][q] += t1[p][q];
+      real vis[P];
+#pragma unroll
+      for (int p = 0; p < P; p++) vis[p] = 0;
+#pragma unroll 1
+      for (int c = 0; c < KX_NUC; c++) {
+        const real* __restrict__ cu = acquire();
+        const int k1 = min(KX_N, (c + 1) * KX_UROWS);
+#pragma unroll 2
+        for (int k = c * KX_UROWS; k < k1; k++, cu += RU) {
+          const real m4 = cu[R + 5];
+          real v[P], w[P], w2[P], ph[P][4];
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            v[p] = kx_quartic(cu + R, lnT[p]);
+            w[p] = v[p] * m4;
+            w2[p] = w[p] * w[p];
+            ph[p][0] = ph[p][1] = ph[p][2] = ph[p][3] = 0;
+          }
+#pragma unroll
+          for (int q = 0; q < R; q += 2) {
+            const real2 uu = *reinterpret_cast<const real2*>(cu + q);
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+              ph[p][q & 2] = fma(uu.x, fma(w2[p], t2[p][q], fma(w[p], t1[p][q], t0[p][q])), ph[p][q & 2]);
+              ph[p][(q & 2) + 1] = fma(uu.y, fma(w2[p], t2[p][q + 1], fma(w[p], t1[p][q + 1], t0[p][q + 1])), ph[p][(q & 2) + 1]);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            const real phi = (ph[p][0] + ph[p][1]) + (ph[p][2] + ph[p][3]);
+            vis[p] = fma(X[k * LDT + p * TT] * (v[p] * v[p]), kx_rcp(phi), vis[p]);
+          }
+        }
+        release();
+      }
+#pragma unroll
+      for (int p = 0; p < P; p++)
+        if (live[p]) kx_st_stream(viscosity + id[p], (ST)(sqrT[p] * vis[p]));
+    }
+
+    // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj over tiles of the lower triangle; the
+    //      coefficients of a pair are fetched once for the P states ----
+#pragma unroll 1
+    for (int kb = 0; kb < KX_NB; kb++) {
+      real xk[P][TB], sk[P][TB];
+#pragma unroll
+      for (int p = 0; p < P; p++)
+#pragma unroll
+        for (int i = 0; i < TB; i++) {
+          const int k = kb * TB + i;
+          xk[p][i] = k < KX_N ? X[x_row(k) + p * TT] : (real)0;
+          sk[p][i] = 0;
+        }
+#pragma unroll 1
+      for (int jb = 0; jb < kb; jb++) {
+        real xj[P][TB], sj[P][TB];
+        unsigned raw[P][2 * TB];
+        // running sums of the column block: requested from tensor memory now, unpacked when the tile has landed
+        kx_tm_wait_st();
+#pragma unroll
+        for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, jb * TB), raw[p]);
+#pragma unroll
+        for (int p = 0; p < P; p++)
+#pragma unroll
+          for (int i = 0; i < TB; i++) xj[p][i] = X[(jb * TB + i) * LDT + p * TT];   // jb < kb: real species
+        const real* __restrict__ tile = acquire();
+        kx_tm_wait_ld();
+#pragma unroll
+        for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], sj[p]);
+#pragma unroll
+        for (int i = 0; i < TB; i++) {
+          real d[P][TB];
 #pragma unroll
           for (int j = 0; j < TB; j++) {
-            if (j & 1) so = fma(xj[p][j], d[p][j], so); else se = fma(xj[p][j], d[p][j], se);
-            sj[p][j] = fma(xk[p][i], d[p][j], sj[p][j]);
+            const real* cp = tile + (i * TB + j) * 5;
+            const real c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+              const real q = fma(c4, lnT4[p], fma(fma(c3, lnT[p], c2), lnT2[p], fma(c1, lnT[p], c0)));
+              d[p][j] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
+            }
           }
-          sk[p][i] += se + so;
-        }
-      }
-      release();
-#pragma unroll
-      for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, jb * TB), sj[p]);
-    }
-    // diagonal tile: pairs i > j inside the block
-    {
-      const real2* __restrict__ tile = reinterpret_cast<const real2*>(acquire());
-#pragma unroll
-      for (int i = 1; i < TB; i++) {
-#pragma unroll
-        for (int j = 0; j < i; j++) {
-          const real2* cp = tile + (i * TB + j) * 3;
-          const real2 c01 = cp[0], c23 = cp[1], c4 = cp[2];
 #pragma unroll
           for (int p = 0; p < P; p++) {
-            const real q = fma(c4.x, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
-            const real d = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
-            sk[p][i] = fma(xk[p][j], d, sk[p][i]);
-            sk[p][j] = fma(xk[p][i], d, sk[p][j]);
+            real se = 0, so = 0;
+#pragma unroll
+            for (int j = 0; j < TB; j++) {
+              if (j & 1) so = fma(xj[p][j], d[p][j], so); else se = fma(xj[p][j], d[p][j], se);
+              sj[p][j] = fma(xk[p][i], d[p][j], sj[p][j]);
+            }
+            sk[p][i] += se + so;
           }
         }
+        release();
+#pragma unroll
+        for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, jb * TB), sj[p]);
       }
-      release();
+      // diagonal tile: pairs i > j inside the block
+      {
+        const real* __restrict__ tile = acquire();
+#pragma unroll
+        for (int i = 1; i < TB; i++) {
+#pragma unroll
+          for (int j = 0; j < i; j++) {
+            const real* cp = tile + (i * TB + j) * 5;
+            const real c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+              const real q = fma(c4, lnT4[p], fma(fma(c3, lnT[p], c2), lnT2[p], fma(c1, lnT[p], c0)));
+              const real d = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
+              sk[p][i] = fma(xk[p][j], d, sk[p][i]);
+              sk[p][j] = fma(xk[p][i], d, sk[p][j]);
+            }
+          }
+        }
+        release();
+      }
+      // first touch of this row block's sums (they replace b_k): later row blocks add their column contributions
+#pragma unroll
+      for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, kb * TB), sk[p]);
     }
-    // first touch of this row block's sums (they replace b_k): later row blocks add their column contributions
-#pragma unroll
-    for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, kb * TB), sk[p]);
-  }
-  kx_tm_wait_st();
+    kx_tm_wait_st();
 
-  // ---- rho * D_km  (mix_transport.py:621-622 and transportProps.okl:43-47; p and Mbar cancel) ----
-#pragma unroll 1
-  for (int kb = 0; kb < KX_NB; kb++) {
-    unsigned raw[P][2 * TB];
-    real s[P][TB];
+    // ---- rho * D_km  (mix_transport.py:621-622 and transportProps.okl:43-47; p and Mbar cancel) ----
 #pragma unroll
-    for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, kb * TB), raw[p]);
-    kx_tm_wait_ld();
+    for (int kb = 0; kb < KX_NB; kb++) {
+      unsigned raw[P][2 * TB];
+      real s[P][TB];
 #pragma unroll
-    for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], s[p]);
+      for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, kb * TB), raw[p]);
+      kx_tm_wait_ld();
 #pragma unroll
-    for (int p = 0; p < P; p++) {
-      const real f = sqrT[p] * (real)(1.0 / 8.31446261815324);      // rho*T^1.5/(p*Mbar) = sqrt(T)/R
+      for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], s[p]);
 #pragma unroll
-      for (int i = 0; i < TB; i++) {
-        const int k = kb * TB + i;
-        if (k < KX_N) {
-          const real num = fma(-kx_M[k], X[k * LD + p * G], Mbar[p]);
-          const real v = f * num * kx_rcp(s[p][i]);
-          if (live[p]) kx_st_stream(rhoD + id[p] + (size_t)k * offset, (ST)v);
+      for (int p = 0; p < P; p++) {
+        const real f = sqrT[p] * (real)(1.0 / 8.31446261815324);      // rho*T^1.5/(p*Mbar) = sqrt(T)/R
+#pragma unroll
+        for (int i = 0; i < TB; i++) {
+          const int k = kb * TB + i;
+          if (k < KX_N) {
+            const real num = fma(-kx_M[k], X[k * LDT + p * TT], Mbar[p]);
+            const real v = f * num * kx_rcp(s[p][i]);
+            if (live[p]) kx_st_stream(rhoD + id[p] + (size_t)k * offset, (ST)v);
+          }
         }
       }
     }

@@ -83,6 +83,54 @@ def test_emitter_produces_a_module(name):
         assert f'  // {i + 1}: ' in src32
 
 
+@pytest.mark.parametrize('name', ALL)
+def test_wilke_mass_factor_matrix_is_low_rank(name):
+    """c_kj = (8 (1 + M_k/M_j))^-1/2 (reference mix_transport.py:311-317, 534-553) is a smooth kernel in
+    ln M_k - ln M_j: the SVD factors the BK2 kernels use reproduce every entry to 1e-13 with rank <= 16."""
+    from kinetix_b200.core.emit_module import wilke_low_rank
+    M = np.array(mech(name).molar_masses)
+    U, V, rank = wilke_low_rank(M)
+    C = 1.0 / np.sqrt(8.0 * (1.0 + M[:, None] / M[None, :]))
+    assert U.shape == (len(M), rank) and V.shape == (len(M), rank)
+    assert np.max(np.abs(U @ V.T - C) / C) <= 1e-13
+    assert rank <= 16 and (rank % 2 == 0 or rank == len(M))
+
+
+def _macros(src):
+    import re
+    return {m.group(1): int(m.group(2)) for m in re.finditer(r'#define (KX_\w+) (-?\d+)\n', src)}
+
+
+def test_bk2_kernel_plan():
+    """which BK2 kernel a mechanism gets, and that the plan respects the hardware limits it was made for:
+    227 KB shared memory per CTA, 512 tensor-memory columns per lane, 16-byte bulk-copy granularity."""
+    import re
+    from kinetix_b200.core.transport_fit import fit_transport
+    # GRI-3.0: persistent tensor-memory kernel, two states per thread
+    m = mech('gri30')
+    src, _ = emit_module(m, fit_transport(m))
+    d = _macros(src)
+    assert '#include "kx_bk2_tmem.cuh"' in src and d['KX_P'] == 2 and d['KX_BK2_BLOCK'] == 256 and d['KX_WR'] == 12
+    assert (d['KX_BK2_BLOCK'] // 128) * d['KX_P'] * 2 * d['KX_NS'] <= 512
+    offs = [int(x) for x in re.search(r'kx_chunk_off\[(\d+)\] = \{([^}]*)\}', src).group(2).split(',')]
+    assert len(offs) == d['KX_N_CHUNKS'] + 1 and offs[0] == 0
+    sizes = np.diff(offs)
+    assert (sizes > 0).all() and (sizes % 2 == 0).all() and sizes.max() <= d['KX_CHUNK_MAX']
+    n_tiles = (d['KX_NP'] // d['KX_TB']) * (d['KX_NP'] // d['KX_TB'] + 1) // 2
+    assert d['KX_NSC'] + d['KX_NVC'] + d['KX_NUC'] + n_tiles == d['KX_N_CHUNKS']
+    smem = int(re.search(r'per_cta = (\d+);.*\n  const size_t smem = (\d+);', src).group(2))
+    assert smem <= 227 * 1024
+    assert smem >= (d['KX_TEAMS'] * d['KX_STAGES'] * d['KX_CHUNK_MAX'] + 53 * 512) * 8
+    # small mechanisms keep the one-state-per-thread kernel with the dense Wilke matrix
+    m = mech('LiDryer')
+    src, _ = emit_module(m, fit_transport(m))
+    assert '#include "kx_bk2.cuh"' in src and 'KX_WR' not in _macros(src)
+    # the --single-precision module keeps the one-state-per-thread kernel too (tensor-memory kernel is FP64)
+    m = mech('gri30')
+    src, _ = emit_module(m, fit_transport(m), single_precision=True)
+    assert '#include "kx_bk2.cuh"' in src and _macros(src)['KX_WR'] == 12
+
+
 def test_tile_choice():
     assert choose_tile(53) == (9, 54)
     assert choose_tile(9) == (9, 9)
