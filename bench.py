@@ -35,6 +35,11 @@ P_ATM = 101325.0
 # Algorithmic FP64-pipe work per state (lane instructions: DFMA/DMUL/DADD), minimal form with the
 # reference's libdevice-class costs -- SURVEY.md 8(d), derivation in DESIGN.md "Roofline".
 W_FP64 = {'gri30': {'bk1': 1.4e4, 'bk2': 2.47e4}}
+# FP64-pipe lane instructions our kernels actually EXECUTE per state (ncu smsp__inst_executed_pipe_fp64 x 32 / states,
+# profiles/ncu_r01_bk1_v6.txt, ncu_r01_bk2_v4.txt): fewer than W (shared exps in BK1; rank-12 Wilke factorisation and
+# the 2-instruction pair reciprocal in BK2), so `frac` (by W) exceeds the hardware-side pipe utilisation,
+# which is reported next to it as `frac_executed`.
+EXEC_FP64 = {'gri30': {'bk1': 1.13e4, 'bk2': 1.82e4}}
 
 
 def read_json(path):
@@ -396,8 +401,11 @@ def main():
     def fp64_roofline(kernel, rate):
         ach = rate * W[kernel] * 2 / 1e12        # FP64 TFLOP/s counting one lane instruction as 2 flop (DFMA)
         pk = peak * 2 / 1e12
-        return {'bound': 'fp64', 'kernel': f'kx_{kernel}_f64', 'achieved': ach, 'peak': pk, 'unit': 'TFLOP/s',
+        return {'bound': 'fp64', 'kernel': 'kx_bk1_f64' if kernel == 'bk1' else 'kx_bk2<double>', 'achieved': ach, 'peak': pk, 'unit': 'TFLOP/s',
                 'frac': ach / pk, 'traffic': traffic(kernel), 'fp64_lane_instr_per_state': W[kernel],
+                'executed_fp64_lane_instr_per_state': EXEC_FP64.get(args.mechanism, {}).get(kernel),
+                'frac_executed': (rate * EXEC_FP64[args.mechanism][kernel] / peak
+                                  if args.mechanism in EXEC_FP64 else None),
                 'states_per_s': rate, 'roofline_states_per_s': peak / W[kernel], 'peak_source': peak_src,
                 'hbm': {'achieved': rate * alg_bytes[kernel] / 1e9, 'peak': hbm, 'unit': 'GB/s',
                         'frac': rate * alg_bytes[kernel] / 1e9 / hbm, 'bytes_per_state': alg_bytes[kernel],

@@ -14,8 +14,8 @@ FP64 = ('DFMA', 'DMUL', 'DADD', 'DSETP')
 def main(path, phases):
     raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    d = dict(zip(rows[0], rows[2]))
-    cycles = float(d['smsp__cycles_active.sum'])
+    ci = rows[0].index('smsp__cycles_active.sum')
+    cycles = sum(float(r[ci]) for r in rows[2:] if len(r) > ci and r[ci])   # the source page sums all launches in the report
     src = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--print-source', 'cuda,sass'],
                          stdout=subprocess.PIPE, text=True).stdout.splitlines()
     ph = sorted((int(a.split(':')[0]), a.split(':')[1]) for a in phases)
@@ -58,6 +58,10 @@ def main(path, phases):
         if op in ('LDS', 'STS', 'LDG', 'STG'):
             lds[name] += n
     tot = sum(samp.values())
+    # normalise to the measured pipe utilisation (reports with several launches aggregate differently per page)
+    pi = rows[0].index('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')
+    measured = [float(r[pi]) for r in rows[2:] if len(r) > pi and r[pi]]
+    cycles *= (100 * 2 * sum(f64.values()) / cycles) / (sum(measured) / len(measured))
     print(f'{"phase":14s} {"time%":>6s} {"fp64 util%":>10s} {"fp64 instr%":>11s} {"instr/fp64":>10s} {"ld/st per fp64":>14s}')
     for n in sorted(samp, key=lambda x: -samp[x]):
         t = samp[n] / tot * cycles
