@@ -362,6 +362,9 @@ class BK1Emitter:
         if gibbs_in_smem or ring:
             w('extern __shared__ double kx_sm[];')
             w('double* const gs = kx_sm + threadIdx.x;')
+        w('#ifdef KX_EXP_TABLE')
+        w('kx_exptab_init();')
+        w('#endif')
         # third-body sums M_i (and ln M_i) are needed all along the reaction list: in shared memory they do not
         # occupy 2 registers each for the whole kernel (GRI-3.0: 10 + 5 values, EtOHKonnov: 30 + 15)
         eff_smem = bool(eff_in_smem and gibbs_in_smem)

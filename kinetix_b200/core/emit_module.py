@@ -436,6 +436,10 @@ def emit_module(mech, fits, options=None, single_precision=False):
     out.append(f'// mechanism: {mech.name}  species: {N} (active {mech.n_active})  reactions: {mech.n_reactions}')
     out.append('#include <cuda_runtime.h>')
     out.append('#include <math_constants.h>')
+    # 32-entry table exp in BK1 (csrc/kx_math.cuh): 17 % fewer FP64 instructions but measured SLOWER on GRI-3.0
+    # (879 vs 909 M states/s: more spills at 168 registers, and the kernel is issue/latency bound, not FP64 bound)
+    if opt.get('exp_table', False) and not sp:
+        out.append('#define KX_EXP_TABLE 1')
     out.append('#include "kx_math.cuh"')
     out.append(f'#define KX_N {N}')
     for d in opt.get('defines', ()):               # development switches (tools/build_variants.py)

@@ -43,12 +43,59 @@ KX_DEVICE double kx_rcp_fast(double a)
 KX_DEVICE double kx_div(double a, double b) { return a * kx_rcp(b); }
 
 // ---- exp -------------------------------------------------------------------------------------
+#ifdef KX_EXP_TABLE
+// Table-driven exp for the kernels that define KX_EXP_TABLE (BK1, FP64):  x = n ln2/32 + r,  |r| <= ln2/64,
+// e^x = 2^(n >> 5) * 2^((n & 31)/32) * e^r  with a degree-5 polynomial for e^r (near-minimax, max relative error
+// 2.5e-16, tools/fit_math_polys.py `expt32`) and a 32-entry table of 2^(j/32) in shared memory: 10 FP64-pipe
+// instructions instead of 15, plus one LDS (lanes pick different entries: at worst a 2-way bank conflict on a pipe
+// this kernel leaves 90 % idle) and three integer instructions.  The table is read at the END of the dependency
+// chain, so its latency is hidden behind the polynomial.
+__constant__ double kx_exptab_c[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
+    1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
+    1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072,
+    1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002};
+__shared__ double kx_exptab[32];
+// every thread of the CTA calls this once, before the first exp
+__device__ __forceinline__ void kx_exptab_init()
+{
+  if (threadIdx.x < 32) kx_exptab[threadIdx.x] = kx_exptab_c[threadIdx.x];
+  __syncthreads();
+}
+__device__ __forceinline__ double kx_exp_table_core(double x, int lo_clamp, int hi_clamp, bool clamp)
+{
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
+  double kd = fma(x, 46.16624130844683, MAGIC);            // 32 / ln 2
+  int n = __double2loint(kd);
+  kd -= MAGIC;
+  double r = fma(kd, -6.93147180369123816490e-01 / 32.0, x);   // (ln2 / 32) high part, exact product
+  r = fma(kd, -1.90821492927058770002e-10 / 32.0, r);          // low part
+  const double t = kx_exptab[n & 31];
+  double s = 0.008333368243545858;
+  s = fma(s, r, 0.04166691103828231);
+  s = fma(s, r, 0.16666666666513108);
+  s = fma(s, r, 0.4999999999892509);
+  s = fma(s, r, 1.0);
+  const double y = fma(t, s * r, t);
+  int k = n >> 5;
+  if (clamp) k = max(min(k, hi_clamp), lo_clamp);
+  return __hiloint2double(__double2hiint(y) + (k << 20), __double2loint(y));
+}
+#endif
+
 // exp(x), x finite.  The exponent is clamped to the normal range with two integer min/max (ALU pipe),
 // so results saturate at ~2^-1022 / ~2^1023 instead of going through denormals / inf: absolute
 // differences of < 1e-307 against libm.  The emitter proves |x| < 700 for every call it routes here
 // over the validity range of T (interval arithmetic at generation time) and uses kx_exp_wide otherwise.
 KX_DEVICE double kx_exp(double x)
 {
+#ifdef KX_EXP_TABLE
+  return kx_exp_table_core(x, -1021, 1022, true);
+#endif
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
   double kd = fma(x, 1.4426950408889634, MAGIC);
   int k = __double2loint(kd);
@@ -75,6 +122,9 @@ KX_DEVICE double kx_exp(double x)
 // clamp at all (14 FP64 + 3 integer instructions).
 KX_DEVICE double kx_exp_nc(double x)
 {
+#ifdef KX_EXP_TABLE
+  return kx_exp_table_core(x, 0, 0, false);
+#endif
   const double MAGIC = 6755399441055744.0;
   double kd = fma(x, 1.4426950408889634, MAGIC);
   const int k = __double2loint(kd);
