@@ -250,6 +250,27 @@ def _claim_stdout():
     return real
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's threads to the CPUs NVML reports as local to its GPU, BEFORE the pinned host buffers of the
+    end-to-end leg are allocated (first touch puts them on that NUMA node): what `mpirun --bind-to` / numactl does
+    for the reference's MPI ranks.  Returns a description for the JSON line, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        index = int(visible.split(',')[local]) if visible and visible.split(',')[local].isdigit() else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        cpus = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f'{len(cpus)} CPUs local to GPU {index}'
+    except Exception:
+        pass
+    return None
+
+
 def main():
     real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -276,6 +297,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the product has no CPU path (use --impl reference)')
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+    numa = bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -429,8 +452,11 @@ def main():
         'gpu_launches': 2 * args.steps,
         'clocks': clocks,
         'module': os.path.relpath(kinetix.modulePath(), ROOT),
+        'host_binding': numa,
     }
     if world == 1 and not args.no_cpu_baseline:
+        if all_cpus:
+            os.sched_setaffinity(0, all_cpus)      # the CPU baseline runs on ALL host cores, not the GPU-local ones
         try:
             line['cpu_baseline'] = cpu_baseline(args.mechanism)
         except Exception as e:     # the baseline is reported, never required for the product number

@@ -10,11 +10,12 @@ sys.path.insert(0, ROOT)
 import kinetix_b200.host as kinetix  # noqa: E402
 from oracle.port import synthetic_states  # noqa: E402
 
-for mech, sp in (('gri30', False), ('LiDryer', False), ('LiDryer', True)):
+# gri30 / heptaneLu88: tensor-memory BK2 kernel (256 / 128 threads); LiDryer: one-state-per-thread kernel; sp: FP32
+for mech, sp in (('gri30', False), ('heptaneLu88', False), ('LiDryer', False), ('LiDryer', True)):
     kinetix.init(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech + '.yaml'), single_precision=sp)
     N = kinetix.nSpecies()
     kinetix.build(101325.0, 1.0, [1.0 / N] * N, True)
-    S = 777
+    S = 1555      # more than one persistent-CTA round of 512 states, ragged tail
     st = torch.from_numpy(synthetic_states(N, S)).cuda()
     r = torch.empty_like(st)
     v = torch.empty(S, dtype=torch.float64, device='cuda')
