@@ -50,10 +50,10 @@ struct State {
   double ref_pressure = 0, ref_temperature = 0, ref_mean_molar_mass = 0;
   std::vector<double> ref_mass_fractions;
   // staging for the host-buffer entry points
-  static const int SLOTS = 3;
-  cudaStream_t streams[SLOTS] = {nullptr, nullptr, nullptr};
-  void* d_in[SLOTS] = {nullptr, nullptr, nullptr};
-  void* d_out[SLOTS] = {nullptr, nullptr, nullptr};
+  static const int SLOTS = 4;
+  cudaStream_t streams[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  void* d_in[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  void* d_out[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   size_t in_bytes = 0, out_bytes = 0;
 } g;
 
@@ -318,7 +318,21 @@ int kx_thermodynamic_props(int64_t n_states, int64_t offsetT, int64_t offset, do
 // ---- host-buffer entry points ---------------------------------------------------------------------
 namespace {
 
-const int64_t CHUNK = 1 << 19;   // states per pipelined chunk (3 slots in flight: H2D | kernels | D2H)
+// states per pipelined chunk (SLOTS chunks in flight: H2D | kernels | D2H).  The copies dominate (PCIe), so the
+// chunk only has to be large enough for full-rate DMA (tens of MB) and small enough that the pipeline's fill and
+// drain (one chunk up, one chunk down) stay a small fraction of a call: 128 Ki states = 55 MB of GRI-3.0 state.
+// KX_HOST_CHUNK overrides (development).
+int64_t host_chunk()
+{
+  static int64_t chunk = 0;
+  if (!chunk) {
+    const char* e = getenv("KX_HOST_CHUNK");
+    chunk = e ? atoll(e) : (int64_t)1 << 17;
+    if (chunk < 1024) chunk = 1024;
+  }
+  return chunk;
+}
+#define CHUNK host_chunk()
 
 int ensure_staging(size_t in_bytes, size_t out_bytes)
 {
