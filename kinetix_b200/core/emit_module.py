@@ -249,7 +249,6 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     FP64).  Returns (smem bytes, states per CTA round, persistent=True) or None when the mechanism does not fit."""
     N = mech.n_species
     M = mech.molar_masses
-    spt = opt.get('bk2_spt', 2)
     tb, NP = choose_tile(N, opt.get('tile_bk2'))
     NB = NP // tb
     U, V, rank = wilke_low_rank(M)
@@ -263,8 +262,14 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
         return tb * min(NB, max(1, cmax0 // (tb * width)))
     srows, vrows, urows = rows(12), rows(wr), rows(wr + 6)
     cmax = -(-max(dchunk, srows * 12, vrows * wr, urows * (wr + 6)) // 2) * 2
+    # (threads, states per thread) in order of measured preference: 8 warps before 4, two states per thread (half
+    # the coefficient wavefronts per state) before one.  heptaneLu88 (88 species): 256 x 1 gives 236, 128 x 2 197 M
+    # states/s; EtOHKonnov (129 species) only fits 128 x 1 (97 vs 72 M for the shared-memory kernel).
     plan = None
-    for threads in (256, 128):
+    shapes = [(256, 2), (256, 1), (128, 2), (128, 1)]
+    if opt.get('bk2_spt'):
+        shapes = [sh for sh in shapes if sh[1] == opt['bk2_spt']]
+    for threads, spt in shapes:
         if (threads // 128) * spt * 2 * ns > 512:  # columns per TMEM lane
             continue
         # two half-CTA teams with skewed phases were measured SLOWER (549 vs 608 M states/s on GRI-3.0): the teams
@@ -275,7 +280,7 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
             for stages in ((opt['bk2_stages'],) if opt.get('bk2_stages') else (4, 2)):
                 smem = 16 * stages * teams + 16 + (teams * stages * cmax + N * threads * spt) * 8
                 if smem <= limit:
-                    plan = (threads, teams, stages, smem)
+                    plan = (threads, teams, stages, smem, spt)
                     break
             if plan:
                 break
@@ -285,7 +290,7 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     # one-state-per-thread kernel (LiDryer 10.4 vs 7.9, gri30-20 2.96 vs 2.71 G states/s)
     if plan is None or plan[0] < opt.get('bk2_tmem_min_threads', 128) or N < opt.get('bk2_tmem_min_species', 25):
         return None
-    threads, teams, stages, smem = plan
+    threads, teams, stages, smem, spt = plan
 
     # the coefficient stream of one batch, chunk by chunk (each chunk padded to a 16-byte multiple)
     stream, offs = [], [0]
@@ -478,7 +483,7 @@ def emit_module(mech, fits, options=None, single_precision=False):
         # get few resident states per SM; 2 or 4 lanes per state bring the resident warps back up
         lanes = opt.get('bk2_lanes') or 1          # lanes > 1 measured slower on GRI-3.0 (profiles/): opt-in
         planned = None
-        if opt.get('bk2_tmem', True) and not sp and lanes == 1 and opt.get('bk2_spt', 2) == 2 and not opt.get('bk2_ring'):
+        if opt.get('bk2_tmem', True) and not sp and lanes == 1 and opt.get('bk2_spt', 2) in (1, 2) and not opt.get('bk2_ring'):
             planned = _emit_bk2_tmem(out, mech, fits, opt, tq)
         bk2_persistent = False
         if planned:
