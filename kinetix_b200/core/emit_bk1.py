@@ -119,9 +119,12 @@ class BK1Emitter:
     def nasa_select(self, k, make):
         """coefficient list for species k selected on T <= T_mid; `make(a)` maps the 7 NASA
         coefficients to the derived coefficients actually needed.
-        nasa_indexed: the low-range sets of all species live in the first half of one __constant__ table and
-        the high-range sets in the second half; a per-T_mid integer offset (0 or half) picks the range, so a
-        coefficient is ONE constant load with a register offset instead of two loads and a 64-bit select."""
+        nasa_indexed: the low-range sets of all species live in the first half of one table and the high-range
+        sets in the second half; a per-T_mid integer offset (0 or half) picks the range, so a coefficient is ONE
+        load with a register offset instead of two loads and a 64-bit select.  The offset differs between the
+        lanes of a warp, so where the table lives matters (GRI-3.0, M states/s): 'ldg' = global memory through L1
+        958 (default), 'smem' = per-CTA copy in shared memory 945, True / 'const' = __constant__ (the load
+        serialises over the two addresses and misses the 2 KB constant cache) 907; 128-bit LDG pairs 936."""
         s = self.m.species[k]
         lo, hi = make(s.nasa_lo), make(s.nasa_hi)
         if getattr(self, 'nasa_indexed', False):
@@ -129,6 +132,11 @@ class BK1Emitter:
             self.nasa_lo_tab += [float(v) for v in lo]
             self.nasa_hi_tab += [float(v) for v in hi]
             off = self.tmid_offset(s.T_mid)
+            mode = self.nasa_indexed
+            if mode == 'ldg':        # global memory through L1 (two addresses per warp at most)
+                return [f'__ldg(&kx_nasa_tab[{off} + {base + i}])' for i in range(len(lo))], lo, hi
+            if mode == 'smem':       # CTA-local copy in shared memory (filled in the kernel prologue)
+                return [f'kx_nasa_s[{off} + {base + i}]' for i in range(len(lo))], lo, hi
             return [f'kx_nasa_tab[{off} + {base + i}]' for i in range(len(lo))], lo, hi
         flag = self.tmid_flag(s.T_mid)
         out = []
@@ -147,8 +155,9 @@ class BK1Emitter:
             return ''
         vals = self.nasa_lo_tab + self.nasa_hi_tab
         body = ',\n  '.join(', '.join(_lit(v) for v in vals[i:i + 4]) for i in range(0, len(vals), 4))
-        return (f'#define KX_NASA_HALF {len(self.nasa_lo_tab)}\n'
-                f'__constant__ double kx_nasa_tab[{len(vals)}] = {{\n  {body}\n}};\n')
+        qual = '__constant__' if self.nasa_indexed in (True, 'const') else '__device__ const __align__(16)'
+        return (f'#define KX_NASA_HALF {len(self.nasa_lo_tab)}\n#define KX_NASA_LEN {len(vals)}\n'
+                f'{qual} double kx_nasa_tab[{len(vals)}] = {{\n  {body}\n}};\n')
 
     def tmid_flag(self, tmid):
         name = 'lo_' + repr(float(tmid)).replace('.', '_').replace('-', 'm')
@@ -365,6 +374,10 @@ class BK1Emitter:
         w('#ifdef KX_EXP_TABLE')
         w('kx_exptab_init();')
         w('#endif')
+        if nasa_indexed == 'smem':
+            w('__shared__ double kx_nasa_s[KX_NASA_LEN];')
+            w('for (int i = threadIdx.x; i < KX_NASA_LEN; i += blockDim.x) kx_nasa_s[i] = kx_nasa_tab[i];')
+            w('__syncthreads();')
         # third-body sums M_i (and ln M_i) are needed all along the reaction list: in shared memory they do not
         # occupy 2 registers each for the whole kernel (GRI-3.0: 10 + 5 values, EtOHKonnov: 30 + 15)
         eff_smem = bool(eff_in_smem and gibbs_in_smem)

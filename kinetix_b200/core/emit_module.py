@@ -195,9 +195,7 @@ def _emit_bk2_lanes(out, mech, fits, opt, lanes, rsize, tq):
         stages, threads = 2, fit(2)                # the ring must not cost a warp
     threads = opt.get('bk2_threads', threads)
     states = threads // lanes * spt
-    smem = 16 * stages + (stages * cmax + 2 * NP * (states // spt if opt.get('bk2_alias') else states)) * rsize
-    if opt.get('bk2_alias'):
-        out.append('#define KX_WHATIF_ALIAS 1')
+    smem = 16 * stages + (stages * cmax + 2 * NP * states) * rsize
     out.append(f'#define KX_TB {tb}')
     out.append(f'#define KX_NP {NP}')
     out.append(f'#define KX_L {lanes}')
@@ -404,7 +402,7 @@ def emit_module(mech, fits, options=None, single_precision=False):
     sp = bool(single_precision)
     rsize = 4 if sp else 8
     opt = dict(block_bk1=128, minb_bk1=3, sync_every=16, gibbs_in_smem=True, reorder=True, prefetch=4, ring=0, pin_loads=False,
-               inline_constants=False, param_constants=True, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=True,
+               inline_constants=False, param_constants=True, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed='ldg',
                block_bk2=128, minb_bk2=2, bk2_scratch=False, bk2_split=2)
     opt.update(options or {})
     N = mech.n_species

@@ -1,5 +1,10 @@
 // kx_bk2_lanes.cuh -- BK2 (mixture-averaged conductivity, viscosity, rho*D_km) with KX_L lanes per state.
 //
+// STATUS: opt-in variant (emit option bk2_lanes = 2 | 4), parity-tested (tests/test_parity_gpu.py) but NOT the
+// default: on the B200 it is slower than both the one-state-per-thread kernel and the tensor-memory kernel
+// (GRI-3.0: 336 / 310 vs 446 / 610 M states/s; EtOHKonnov 50 / 31 vs 57 / 97) because the pair loops are bound by
+// shared-memory wavefronts, not by occupancy: more warps issue the same coefficient loads.
+//
 // Same arithmetic as csrc/kx_bk2.cuh (reference benchmark/okl/transportProps.okl:11-49 around
 // kinetix/core/mix_transport.py:474-626); what changes is the mapping of work to threads.
 //
@@ -101,11 +106,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   extern __shared__ __align__(16) unsigned char kx_sm_raw[];
   // G groups of L lanes; every group carries P states (slots g, g + G, ...): LD = G * P states per CTA
   constexpr int L = KX_L, P = KX_P, CJ = KX_TB / L, MJ = KX_NP / L;
-#ifdef KX_WHATIF_ALIAS   // timing experiment only (wrong results): the P states of a group share one shared-memory slot
-  constexpr int GS = KX_BK2_BLOCK / L, G = 0, LD = GS;
-#else
   constexpr int GS = KX_BK2_BLOCK / L, G = GS, LD = GS * P;
-#endif
   constexpr int NW = KX_BK2_BLOCK / 32, STG = KX_STAGES;
   constexpr int N_CHUNKS = KX_NB + KX_N_DTILES;
   static_assert(KX_TB % L == 0 && (STG & (STG - 1)) == 0, "tile / ring shape");

@@ -134,6 +134,29 @@ def test_bk2_matches_oracle_on_random_states(kinetix, mech):
     assert max(errs) <= TOL
 
 
+@pytest.mark.parametrize('variant', ['single', 'single_dense', 'lanes2', 'teams2', 'tmem_p1'])
+def test_bk2_kernel_variants_match_oracle(kinetix, variant):
+    """the opt-in BK2 kernels (prebuilt by __graft_entry__.build() from the same emitter with different options:
+    one state per thread with / without the low-rank Wilke factorisation, two lanes per state, the tensor-memory
+    kernel with two teams / one state per thread) compute the same transport properties as the default kernel's
+    oracle; ragged size: several persistent-CTA rounds plus a partial batch."""
+    import __graft_entry__ as entry
+    lib = os.path.join(entry.variant_dir(variant), 'libkx_mech.so')
+    if not os.path.exists(lib):
+        pytest.skip(f'variant module {variant} not prebuilt')
+    kinetix.init(mech_path('gri30'), cache_dir=os.path.dirname(entry.variant_dir(variant)))
+    assert os.path.samefile(kinetix.modulePath(), lib)
+    N = kinetix.nSpecies()
+    kinetix.build(P_ATM, 1.0, [1.0 / N] * N, True)
+    orc = Oracle('gri30')
+    st = synthetic_states(N, 4 * 512 + 333, seed=99)
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    errs = rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)
+    print(f'{variant}: cond {errs[0]:.3e} visc {errs[1]:.3e} rhoD {errs[2]:.3e}')
+    assert max(errs) <= TOL
+
+
 @pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
 def test_thermo_matches_oracle(kinetix, mech):
     N = _setup(kinetix, mech)
