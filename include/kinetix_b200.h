@@ -84,6 +84,17 @@ int kx_thermodynamic_props(int64_t n_states, int64_t offsetT, int64_t offset, do
                            const void* d_state, void* d_rho, void* d_cp_i, void* d_rho_cp,
                            int dtype, void* cuda_stream);
 
+/* Extension beyond the reference: one pressure PER STATE instead of one per launch
+ * (kinetix.cpp:802-812 dimensionalises a single scalar).  d_pressure[id] = p / p_ref, n_states entries of the
+ * same storage type as the state.  With a constant field these compute exactly what kx_production_rates /
+ * kx_thermodynamic_props compute with that scalar.  The transport properties of kx_mixture_avg_transport_props
+ * do not depend on pressure at all (p cancels in rho * D_km, transportProps.okl:41-46), so it has no such flavour. */
+int kx_production_rates_pfield(int64_t n_states, int64_t offsetT, int64_t offset, const void* d_pressure,
+                               const void* d_state, void* d_rates, int dtype, void* cuda_stream);
+int kx_thermodynamic_props_pfield(int64_t n_states, int64_t offsetT, int64_t offset, const void* d_pressure,
+                                  const void* d_state, void* d_rho, void* d_cp_i, void* d_rho_cp,
+                                  int dtype, void* cuda_stream);
+
 /* Host-buffer entry points: same arithmetic, HOST pointers in/out (pageable or pinned).  The batch is
  * cut into chunks that are copied in, computed and copied out on alternating streams so that PCIe
  * transfers overlap the kernels.  These are what an application that keeps its fields on the host

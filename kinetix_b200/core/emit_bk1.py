@@ -405,7 +405,7 @@ class BK1Emitter:
             for vec, name in eff_names.items():
                 if vec[k] != 1:
                     w(f'  a{name} = fma({K(vec[k] - 1)}, w{k}, a{name});')
-        w('  rho = pressure_R * rcpT * kx_rcp(rcpMbar);')
+        w('  rho = pR * rcpT * kx_rcp(rcpMbar);')
         w('  Cm = rho * rcpMbar;')
         for name in eff_names.values():
             w(f'  {eff_ref[name]} = fma(rho, a{name}, Cm);')
@@ -680,10 +680,13 @@ class BK1Emitter:
             f'// BK1 (species production rates): {m.name}, {N} species / {m.n_reactions} reactions; '
             f'{self.stats["exp"]} kx_exp, {self.stats["exp_wide"]} wide exp, {self.stats["log"]} log, '
             f'{self.stats["rcp"]} rcp per state; peak live species {peak_live}, {n_slots} smem slots',
-            f'extern "C" __global__ void __launch_bounds__({block}, {min_blocks})',
+            '// PF: per-state pressure field (extension); the reference flavour PF = false carries no trace of it',
+            'template <bool PF>',
+            f'__global__ void __launch_bounds__({block}, {min_blocks})',
             f'{kernel_name}(const long long n_states, const long long offsetT, const long long offset,',
             '           const double pressure_R, const double P, const double lnP,',
-            '           const double* __restrict__ state, double* __restrict__ rates, const double Tref' +
+            '           const double* __restrict__ state, double* __restrict__ rates, const double Tref,',
+            '           const double* __restrict__ pfield' +
             (', const __grid_constant__ KxParamPool kp)' if getattr(K, 'as_param', False) else ')'),
             '{',
             '  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;',
@@ -691,6 +694,15 @@ class BK1Emitter:
             '  const long long id = live ? gid : n_states - 1;   // tail threads recompute the last state, store nothing',
             '  const double* sp = state + id + offsetT;',
             '  double* out = rates + id + offsetT;',
+            '  // per-state pressure (extension; the reference has one pressure per launch, kinetix.cpp:802-812):',
+            '  // pfield[id] = p / p_ref of this state, the scalar arguments then carry p_ref',
+            '  double pR = pressure_R, Pv = P, lnPv = lnP;',
+            '  if (PF) {',
+            '    const double pn = kx_ld_stream(pfield + id);',
+            '    pR *= pn;',
+            '    Pv *= pn;',
+            f'    lnPv = {"kx_log(Pv)" if any(r.kind == "P-log" for r in m.reactions) else "lnP"};',
+            '  }',
         ]
         return '\n'.join(head + body + ['}', ''])
 
@@ -739,18 +751,18 @@ class BK1Emitter:
         for i in range(n - 1):
             (p1, k1), (p2, k2) = pl[i], pl[i + 1]
             lnp1, lnp2 = math.log(p1), math.log(p2)
-            w(f'    {"if" if i == 0 else "} else if"} ((P > {_lit(p1)}) && (P < {_lit(p2)})) {{')
+            w(f'    {"if" if i == 0 else "} else if"} ((Pv > {_lit(p1)}) && (Pv < {_lit(p2)})) {{')
             w(f'      const double l1 = kx_log({ksum(k1)}), l2 = kx_log({ksum(k2)});')
-            w(f'      kf = kx_exp(fma((l2 - l1) * (lnP - {K(lnp1)}), {K(1 / (lnp2 - lnp1))}, l1));')
+            w(f'      kf = kx_exp(fma((l2 - l1) * (lnPv - {K(lnp1)}), {K(1 / (lnp2 - lnp1))}, l1));')
             self.stats['log'] += 2
             self.stats['exp'] += 1
             if i == 0:
-                w(f'    }} else if (P <= {_lit(p1)}) {{')
+                w(f'    }} else if (Pv <= {_lit(p1)}) {{')
                 w(f'      kf = {ksum(k1)};')
             else:
-                w(f'    }} else if (P == {_lit(p1)}) {{')
+                w(f'    }} else if (Pv == {_lit(p1)}) {{')
                 w(f'      kf = {ksum(k1)};')
             if i == n - 2:
-                w(f'    }} else if (P >= {_lit(p2)}) {{')
+                w(f'    }} else if (Pv >= {_lit(p2)}) {{')
                 w(f'      kf = {ksum(k2)};')
         w('    } else { kf = 0.0; }')

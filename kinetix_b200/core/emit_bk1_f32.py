@@ -115,7 +115,7 @@ class BK1EmitterF32(BK1Emitter):
                 if vec[k] != 1:
                     w(f'  {name} = fmaf({K(vec[k] - 1)}, w{k}, {name});')
         w('}')
-        w('const float rho = pressure_R * rcpT * kx_rcpf(rcpMbar);')
+        w('const float rho = pR * rcpT * kx_rcpf(rcpMbar);')
         w('const float Cm = rho * rcpMbar;')
         for name in eff_names.values():
             w(f'{name} = fmaf(rho, {name}, Cm);')
@@ -272,17 +272,26 @@ class BK1EmitterF32(BK1Emitter):
         head = [
             f'// BK1, FP32 math (fpmix: S = double, fp32: S = float): {m.name}; {self.stats["exp"]} ex2, '
             f'{self.stats["log"]} lg2, {self.stats["rcp"]} rcp per state; peak live species {peak_live}',
-            'template <typename S>',
+            'template <typename S, bool PF>',
             f'__global__ void __launch_bounds__({block}, {min_blocks})',
             f'{kernel_name}(const long long n_states, const long long offsetT, const long long offset,',
             '           const float pressure_R, const float P, const float lnP,',
-            '           const S* __restrict__ state, S* __restrict__ rates, const double Tref)',
+            '           const S* __restrict__ state, S* __restrict__ rates, const double Tref,',
+            '           const S* __restrict__ pfield)',
             '{',
             '  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;',
             '  const bool live = gid < n_states;',
             '  const long long id = live ? gid : n_states - 1;',
             '  const S* sp = state + id + offsetT;',
             '  S* out = rates + id + offsetT;',
+            '  // per-state pressure (extension): pfield[id] = p / p_ref, the scalars then carry p_ref',
+            '  float pR = pressure_R, Pv = P, lnPv = lnP;',
+            '  if (PF) {',
+            '    const float pn = (float)kx_ld_stream(pfield + id);',
+            '    pR *= pn;',
+            '    Pv *= pn;',
+            f'    lnPv = {"kx_log(Pv)" if any(r.kind == "P-log" for r in m.reactions) else "lnP"};',
+            '  }',
         ]
         return '\n'.join(head + body + ['}', ''])
 
@@ -332,15 +341,15 @@ class BK1EmitterF32(BK1Emitter):
         for i in range(n - 1):
             (p1, k1), (p2, k2) = pl[i], pl[i + 1]
             lnp1, lnp2 = math.log(p1), math.log(p2)
-            w(f'    {"if" if i == 0 else "} else if"} ((P > {_lit(p1)}f) && (P < {_lit(p2)}f)) {{')
+            w(f'    {"if" if i == 0 else "} else if"} ((Pv > {_lit(p1)}f) && (Pv < {_lit(p2)}f)) {{')
             w(f'      const float a1 = {l2sum(k1)}, a2 = {l2sum(k2)};')
-            w(f'      l2k = fmaf((a2 - a1) * (lnP - {K(lnp1)}), {K(1 / (lnp2 - lnp1))}, a1);')
+            w(f'      l2k = fmaf((a2 - a1) * (lnPv - {K(lnp1)}), {K(1 / (lnp2 - lnp1))}, a1);')
             if i == 0:
-                w(f'    }} else if (P <= {_lit(p1)}f) {{')
+                w(f'    }} else if (Pv <= {_lit(p1)}f) {{')
             else:
-                w(f'    }} else if (P == {_lit(p1)}f) {{')
+                w(f'    }} else if (Pv == {_lit(p1)}f) {{')
             w(f'      l2k = {l2sum(k1)};')
             if i == n - 2:
-                w(f'    }} else if (P >= {_lit(p2)}f) {{')
+                w(f'    }} else if (Pv >= {_lit(p2)}f) {{')
                 w(f'      l2k = {l2sum(k2)};')
         w('    } else { l2k = -150.f; }')

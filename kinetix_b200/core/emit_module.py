@@ -17,7 +17,7 @@ from . import constants as const
 from .emit_bk1 import BK1Emitter, ConstPool, _lit
 from .emit_bk1_f32 import BK1EmitterF32, FloatPool
 
-ABI_VERSION = 1
+ABI_VERSION = 2      # 2: per-state pressure field argument in kxm_production_rates / kxm_thermo
 
 
 def _table(name, rows, qualifier='__constant__', dims=None, ctype='real'):
@@ -521,11 +521,15 @@ static int kxm_set_smem(K kernel, size_t smem) {{
         out.append(f'''
 template <typename S>
 static int launch_bk1(long long n, long long offsetT, long long offset, double pressure_R, double pressure,
-                      const void* state, void* rates, double Tref, cudaStream_t stream) {{
+                      const void* state, void* rates, double Tref, const void* pfield, cudaStream_t stream) {{
   const int block = {opt['block_bk1']};
   const unsigned grid = (unsigned)((n + block - 1) / block);
-  kx_bk1_f32<S><<<grid, block, 0, stream>>>(n, offsetT, offset, (float)pressure_R, (float)pressure,
-                                            (float)log(pressure), (const S*)state, (S*)rates, Tref);
+  if (pfield)
+    kx_bk1_f32<S, true><<<grid, block, 0, stream>>>(n, offsetT, offset, (float)pressure_R, (float)pressure,
+                                                    (float)log(pressure), (const S*)state, (S*)rates, Tref, (const S*)pfield);
+  else
+    kx_bk1_f32<S, false><<<grid, block, 0, stream>>>(n, offsetT, offset, (float)pressure_R, (float)pressure,
+                                                     (float)log(pressure), (const S*)state, (S*)rates, Tref, nullptr);
   return (int)cudaGetLastError();
 }}
 ''')
@@ -533,27 +537,36 @@ static int launch_bk1(long long n, long long offsetT, long long offset, double p
         out.append(f'''
 template <typename S>
 static int launch_bk1(long long n, long long offsetT, long long offset, double pressure_R, double pressure,
-                      const void* state, void* rates, double Tref, cudaStream_t stream) {{
+                      const void* state, void* rates, double Tref, const void* pfield, cudaStream_t stream) {{
   const int block = {opt['block_bk1']};
   const size_t smem = {bk1_smem};
   static bool configured = false;
   if (!configured) {{
-    if (int e = kxm_set_smem(kx_bk1_f64, smem)) return e;
+    if (int e = kxm_set_smem(kx_bk1_f64<false>, smem)) return e;
+    if (int e = kxm_set_smem(kx_bk1_f64<true>, smem)) return e;
     configured = true;
   }}
   const unsigned grid = (unsigned)((n + block - 1) / block);
-  kx_bk1_f64<<<grid, block, smem, stream>>>(n, offsetT, offset, pressure_R, pressure, log(pressure),
-                                         (const double*)state, (double*)rates, Tref{', kx_param_pool' if opt['param_constants'] else ''});
+  if (pfield)
+    kx_bk1_f64<true><<<grid, block, smem, stream>>>(n, offsetT, offset, pressure_R, pressure, log(pressure),
+                                                    (const double*)state, (double*)rates, Tref, (const double*)pfield{', kx_param_pool' if opt['param_constants'] else ''});
+  else
+    kx_bk1_f64<false><<<grid, block, smem, stream>>>(n, offsetT, offset, pressure_R, pressure, log(pressure),
+                                                     (const double*)state, (double*)rates, Tref, nullptr{', kx_param_pool' if opt['param_constants'] else ''});
   return (int)cudaGetLastError();
 }}
 ''')
     out.append(f'''
 template <typename S>
 static int launch_thermo(long long n, long long offsetT, long long offset, double pressure_R, const void* state,
-                         void* rho, void* cp, void* rhoCp, double Tref, cudaStream_t stream) {{
+                         void* rho, void* cp, void* rhoCp, double Tref, const void* pfield, cudaStream_t stream) {{
   const unsigned grid = (unsigned)((n + 255) / 256);
-  kx_thermo<S><<<grid, 256, 0, stream>>>(n, offsetT, offset, (real)pressure_R, (const S*)state, (S*)rho, (S*)cp,
-                                         (S*)rhoCp, Tref);
+  if (pfield)
+    kx_thermo<S, true><<<grid, 256, 0, stream>>>(n, offsetT, offset, (real)pressure_R, (const S*)state, (S*)rho,
+                                                 (S*)cp, (S*)rhoCp, Tref, (const S*)pfield);
+  else
+    kx_thermo<S, false><<<grid, 256, 0, stream>>>(n, offsetT, offset, (real)pressure_R, (const S*)state, (S*)rho,
+                                                  (S*)cp, (S*)rhoCp, Tref, nullptr);
   return (int)cudaGetLastError();
 }}
 ''')
@@ -585,13 +598,15 @@ static int launch_bk2(long long n, long long offsetT, long long offset, double p
 }}
 ''')
     f32_case = 'if (dtype == 1) return {fn}<float>({args});' if sp else 'if (dtype == 1) return 1000;'
-    a1 = 'n, offsetT, offset, pressure_R, pressure, state, rates, Tref, stream'
+    a1 = 'n, offsetT, offset, pressure_R, pressure, state, rates, Tref, pfield, stream'
     a2 = 'n, offsetT, offset, pressure, state, conductivity, viscosity, rhoD, Tref, stream'
-    a3 = 'n, offsetT, offset, pressure_R, state, rho, cp, rhoCp, Tref, stream'
+    a3 = 'n, offsetT, offset, pressure_R, state, rho, cp, rhoCp, Tref, pfield, stream'
     out.append(f'''
 extern "C" {{
+// pfield: NULL, or n per-state pressures p / p_ref (storage type of the state); the scalars then carry p_ref
 int kxm_production_rates(long long n, long long offsetT, long long offset, double pressure_R, double pressure,
-                         const void* state, void* rates, double Tref, int dtype, cudaStream_t stream) {{
+                         const void* state, void* rates, double Tref, const void* pfield, int dtype,
+                         cudaStream_t stream) {{
   if (n <= 0) return 0;
   {f32_case.format(fn='launch_bk1', args=a1)}
   if (dtype != 0) return 1000;
@@ -599,7 +614,7 @@ int kxm_production_rates(long long n, long long offsetT, long long offset, doubl
 }}
 
 int kxm_thermo(long long n, long long offsetT, long long offset, double pressure_R, const void* state,
-               void* rho, void* cp, void* rhoCp, double Tref, int dtype, cudaStream_t stream) {{
+               void* rho, void* cp, void* rhoCp, double Tref, const void* pfield, int dtype, cudaStream_t stream) {{
   if (n <= 0) return 0;
   {f32_case.format(fn='launch_thermo', args=a3)}
   if (dtype != 0) return 1000;

@@ -28,12 +28,12 @@ const double R_GAS = 1.380649e-23 * 6.02214076e23;   // kinetix.cpp:37
 typedef int (*fn_int_t)();
 typedef const char* (*fn_str_t)();
 typedef void (*fn_masses_t)(double*);
-typedef int (*fn_rates_t)(long long, long long, long long, double, double, const void*, void*, double, int,
-                          cudaStream_t);
+typedef int (*fn_rates_t)(long long, long long, long long, double, double, const void*, void*, double, const void*,
+                          int, cudaStream_t);
 typedef int (*fn_transport_t)(long long, long long, long long, double, const void*, void*, void*, void*, double,
                               int, cudaStream_t);
-typedef int (*fn_thermo_t)(long long, long long, long long, double, const void*, void*, void*, void*, double, int,
-                           cudaStream_t);
+typedef int (*fn_thermo_t)(long long, long long, long long, double, const void*, void*, void*, void*, double,
+                           const void*, int, cudaStream_t);
 
 struct State {
   void* module = nullptr;
@@ -204,7 +204,7 @@ int kx_init(const char* yaml_path, const kx_options* opt_in)
     unload();
     return fail("kx_init: " + lib + " does not export the kxm_* module interface");
   }
-  if (abi() != 1) {
+  if (abi() != 2) {
     unload();
     return fail("kx_init: module ABI version mismatch, remove the cached module " + lib);
   }
@@ -280,9 +280,24 @@ int kx_production_rates(int64_t n_states, int64_t offsetT, int64_t offset, doubl
   if (int e = check_dtype("kx_production_rates", dtype)) return e;
   const double pressure_ = pressure * g.ref_pressure;          // kinetix.cpp:802-803
   const double pressure_R = pressure_ / R_GAS;
-  int e = g.rates(n_states, offsetT, offset, pressure_R, pressure_, d_state, d_rates, g.ref_temperature, dtype,
-                  (cudaStream_t)stream);
+  int e = g.rates(n_states, offsetT, offset, pressure_R, pressure_, d_state, d_rates, g.ref_temperature, nullptr,
+                  dtype, (cudaStream_t)stream);
   return e ? cuda_fail("kx_production_rates", e) : 0;
+}
+
+// Extension: one pressure PER STATE.  d_pressure[id] = p / p_ref, same storage type as the
+// state.  The reference has a single pressure per launch (kinetix.cpp:802-812); with a constant field this call
+// computes exactly what kx_production_rates computes.
+int kx_production_rates_pfield(int64_t n_states, int64_t offsetT, int64_t offset, const void* d_pressure,
+                               const void* d_state, void* d_rates, int dtype, void* stream)
+{
+  KX_REQUIRE_BUILT("kx_production_rates_pfield");
+  if (n_states < 0) return fail("kx_production_rates_pfield: negative n_states");
+  if (n_states && (!d_state || !d_rates || !d_pressure)) return fail("kx_production_rates_pfield: NULL buffer");
+  if (int e = check_dtype("kx_production_rates_pfield", dtype)) return e;
+  int e = g.rates(n_states, offsetT, offset, g.ref_pressure / R_GAS, g.ref_pressure, d_state, d_rates,
+                  g.ref_temperature, d_pressure, dtype, (cudaStream_t)stream);
+  return e ? cuda_fail("kx_production_rates_pfield", e) : 0;
 }
 
 int kx_mixture_avg_transport_props(int64_t n_states, int64_t offsetT, int64_t offset, double pressure,
@@ -310,9 +325,24 @@ int kx_thermodynamic_props(int64_t n_states, int64_t offsetT, int64_t offset, do
   if (n_states && (!d_state || !d_rho || !d_cp_i || !d_rho_cp)) return fail("kx_thermodynamic_props: NULL buffer");
   if (int e = check_dtype("kx_thermodynamic_props", dtype)) return e;
   const double pressure_R = pressure * g.ref_pressure / R_GAS;   // kinetix.cpp:858
-  int e = g.thermo(n_states, offsetT, offset, pressure_R, d_state, d_rho, d_cp_i, d_rho_cp, g.ref_temperature, dtype,
-                   (cudaStream_t)stream);
+  int e = g.thermo(n_states, offsetT, offset, pressure_R, d_state, d_rho, d_cp_i, d_rho_cp, g.ref_temperature,
+                   nullptr, dtype, (cudaStream_t)stream);
   return e ? cuda_fail("kx_thermodynamic_props", e) : 0;
+}
+
+// per-state pressure flavour of kx_thermodynamic_props (rho = p M / (R T) is the only pressure-dependent output)
+int kx_thermodynamic_props_pfield(int64_t n_states, int64_t offsetT, int64_t offset, const void* d_pressure,
+                                  const void* d_state, void* d_rho, void* d_cp_i, void* d_rho_cp, int dtype,
+                                  void* stream)
+{
+  KX_REQUIRE_BUILT("kx_thermodynamic_props_pfield");
+  if (n_states < 0) return fail("kx_thermodynamic_props_pfield: negative n_states");
+  if (n_states && (!d_state || !d_rho || !d_cp_i || !d_rho_cp || !d_pressure))
+    return fail("kx_thermodynamic_props_pfield: NULL buffer");
+  if (int e = check_dtype("kx_thermodynamic_props_pfield", dtype)) return e;
+  int e = g.thermo(n_states, offsetT, offset, g.ref_pressure / R_GAS, d_state, d_rho, d_cp_i, d_rho_cp,
+                   g.ref_temperature, d_pressure, dtype, (cudaStream_t)stream);
+  return e ? cuda_fail("kx_thermodynamic_props_pfield", e) : 0;
 }
 
 // ---- host-buffer entry points ---------------------------------------------------------------------

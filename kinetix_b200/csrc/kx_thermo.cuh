@@ -12,11 +12,11 @@
 #pragma once
 #include "kx_math.cuh"
 
-template <typename S>
+template <typename S, bool PF>   // PF: per-state pressure field (extension)
 __global__ void __launch_bounds__(256)
 kx_thermo(const long long n_states, const long long offsetT, const long long offset, const real pressure_R,
           const S* __restrict__ state, S* __restrict__ rho, S* __restrict__ cp, S* __restrict__ rhoCp,
-          const double Tref)
+          const double Tref, const S* __restrict__ pfield)
 {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_states) return;
@@ -35,7 +35,9 @@ kx_thermo(const long long n_states, const long long offsetT, const long long off
     rcpMbar += w;
     cpw = fma(cpR, w, cpw);
   }
-  const real rho_ = pressure_R * kx_rcp(T) * kx_rcp(rcpMbar);
+  // per-state pressure (extension): pfield[id] = p / p_ref, pressure_R then carries p_ref / R
+  const real pR = PF ? pressure_R * (real)kx_ld_stream(pfield + id) : pressure_R;
+  const real rho_ = pR * kx_rcp(T) * kx_rcp(rcpMbar);
   kx_st_stream(rho + id, (S)rho_);
   kx_st_stream(rhoCp + id, (S)(rho_ * (R * cpw)));
 }

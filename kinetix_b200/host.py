@@ -53,6 +53,8 @@ def library():
     lib.kx_production_rates.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp, _int, _vp]
     lib.kx_mixture_avg_transport_props.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _int, _vp]
     lib.kx_thermodynamic_props.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _int, _vp]
+    lib.kx_production_rates_pfield.argtypes = [_i64, _i64, _i64, _vp, _vp, _vp, _int, _vp]
+    lib.kx_thermodynamic_props_pfield.argtypes = [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp]
     lib.kx_production_rates_host.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp]
     lib.kx_mixture_avg_transport_props_host.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp, _vp, _vp]
     lib.kx_rates_and_transport_host.argtypes = [_i64, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _vp]
@@ -145,6 +147,22 @@ def thermodynamicProps(n_states, offsetT, offset, pressure, o_state, o_rho, o_cp
     _check(library().kx_thermodynamic_props(n_states, offsetT, offset, pressure, _ptr(o_state), _ptr(o_rho),
                                             _ptr(o_cpi), _ptr(o_rhoCp), dtype, _stream(stream)),
            'kinetix.thermodynamicProps')
+
+
+def productionRatesPressureField(n_states, offsetT, offset, o_pressure, o_state, o_rates, stream=None,
+                                 dtype=KX_DTYPE_F64):
+    """extension: productionRates with one pressure per state, o_pressure[id] = p / p_ref."""
+    _check(library().kx_production_rates_pfield(n_states, offsetT, offset, _ptr(o_pressure), _ptr(o_state),
+                                                _ptr(o_rates), dtype, _stream(stream)),
+           'kinetix.productionRatesPressureField')
+
+
+def thermodynamicPropsPressureField(n_states, offsetT, offset, o_pressure, o_state, o_rho, o_cpi, o_rhoCp,
+                                    stream=None, dtype=KX_DTYPE_F64):
+    """extension: thermodynamicProps with one pressure per state."""
+    _check(library().kx_thermodynamic_props_pfield(n_states, offsetT, offset, _ptr(o_pressure), _ptr(o_state),
+                                                   _ptr(o_rho), _ptr(o_cpi), _ptr(o_rhoCp), dtype, _stream(stream)),
+           'kinetix.thermodynamicPropsPressureField')
 
 
 def productionRatesHost(n_states, offsetT, offset, pressure, h_state, h_rates):

@@ -45,7 +45,8 @@ def test_generated_module_exports_interface():
     mechanism's metadata -- host-side calls only, no kernel launch."""
     d = jit.ensure_module(mech_path('LiDryer'))
     mod = ctypes.CDLL(os.path.join(d, 'libkx_mech.so'))
-    assert mod.kxm_abi_version() == 1
+    from kinetix_b200.core.emit_module import ABI_VERSION
+    assert mod.kxm_abi_version() == ABI_VERSION
     assert mod.kxm_n_species() == 9 and mod.kxm_n_active_species() == 8 and mod.kxm_n_reactions() == 21
     mod.kxm_species_names.restype = ctypes.c_char_p
     names = mod.kxm_species_names().decode().split()

@@ -73,7 +73,7 @@ def test_emitter_produces_a_module(name):
         assert f'  // {i + 1}: ' in src
     assert stats['bk1_schedule']['peak_live'] <= m.n_species
     if any(r.kind == 'P-log' for r in m.reactions):
-        assert 'lnP' in src and 'P >' in src
+        assert 'lnPv' in src and 'Pv >' in src and 'lnPv = kx_log(Pv)' in src
     if any(r.kind == 'SRI' for r in m.reactions):
         assert 'kx_pow' in src
     # the --single-precision flavour of the same mechanism: FP32 kernel template + both storage types

@@ -391,6 +391,47 @@ def test_batch_beyond_32bit_element_indices(kinetix):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize('mech', ['gri30', 'NH3Konnov_edit'])
+def test_per_state_pressure_field(kinetix, mech):
+    """extension: one pressure per state.  States are dealt round-robin to four pressures; every
+    group must match the oracle run at that group's (single, reference-style) pressure -- for NH3Konnov_edit the
+    pressures straddle its P-log tables, so ln P is evaluated per state -- and a constant field must reproduce the
+    scalar call (to rounding: p_ref/R * p instead of (p_ref * p)/R)."""
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech, prefer_ref=(mech == 'gri30'))
+    S = 4000
+    st = synthetic_states(N, S, seed=77)
+    p_nd = np.array([0.3, 1.0, 7.0, 40.0])
+    field = np.ascontiguousarray(p_nd[np.arange(S) % 4])
+    d_state = torch.from_numpy(st).cuda()
+    d_p = torch.from_numpy(field).cuda()
+    d_rates = torch.full_like(d_state, float('nan'))
+    kinetix.productionRatesPressureField(S, S, S, d_p, d_state, d_rates)
+    rho = torch.full((S,), float('nan'), dtype=torch.float64, device='cuda')
+    rhocp = torch.full_like(rho, float('nan'))
+    cpi = torch.full((N, S), float('nan'), dtype=torch.float64, device='cuda')
+    kinetix.thermodynamicPropsPressureField(S, S, S, d_p, d_state, rho, cpi, rhocp)
+    torch.cuda.synchronize()
+    new, rho, rhocp, cpi = d_rates.cpu().numpy(), rho.cpu().numpy(), rhocp.cpu().numpy(), cpi.cpu().numpy()
+    for g, pn in enumerate(p_nd):
+        sel = np.arange(S) % 4 == g
+        sub = np.ascontiguousarray(st[:, sel])
+        ref = orc.production_rates(sub, pn * P_ATM)
+        rate_err, hrr_err = bk1_errors(np.ascontiguousarray(new[:, sel]), ref)
+        r_rho, r_cp, r_rhocp = orc.thermo(sub, pn * P_ATM)
+        e3 = max(rel_err(rho[sel], r_rho), rel_err(cpi[:, sel], r_cp), rel_err(rhocp[sel], r_rhocp))
+        print(f'{mech} p = {pn} atm: BK1 {rate_err:.2e} hrr {hrr_err:.2e} thermo {e3:.2e}')
+        assert rate_err <= TOL and hrr_err <= TOL and e3 <= TOL
+    # constant field == scalar pressure
+    d_p.fill_(7.0)
+    kinetix.productionRatesPressureField(S, S, S, d_p, d_state, d_rates)
+    d_ref = torch.empty_like(d_rates)
+    kinetix.productionRates(S, S, S, 7.0, d_state, d_ref)
+    torch.cuda.synchronize()
+    e_rate, e_hrr = bk1_errors(d_rates.cpu().numpy(), d_ref.cpu().numpy())
+    assert e_rate <= 1e-13 and e_hrr <= 1e-13
+
+
 def test_errors_are_loud(kinetix):
     kinetix.finalize()
     with pytest.raises(kinetix.KinetixError):
