@@ -280,7 +280,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--mechanism', default='gri30')
     ap.add_argument('--n-states', type=int, default=1 << 24, help='states per GPU')
-    ap.add_argument('--e2e-states', type=int, default=1 << 21, help='states per GPU per end-to-end step')
+    ap.add_argument('--e2e-states', type=int, default=1 << 22, help='states per GPU per end-to-end step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

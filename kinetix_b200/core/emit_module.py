@@ -289,6 +289,9 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     if plan is None or plan[0] < opt.get('bk2_tmem_min_threads', 128) or N < opt.get('bk2_tmem_min_species', 25):
         return None
     threads, teams, stages, smem, spt = plan
+    # every CTA allocates all 512 tensor-memory columns of its SM: never let two of them share an SM (the second
+    # would wait in tcgen05.alloc until the first, persistent, CTA exits)
+    smem = max(smem, 117 * 1024)
 
     # the coefficient stream of one batch, chunk by chunk (each chunk padded to a 16-byte multiple)
     stream, offs = [], [0]
@@ -443,10 +446,10 @@ def emit_module(mech, fits, options=None, single_precision=False):
     # (879 vs 909 M states/s: more spills at 168 registers, and the kernel is issue/latency bound, not FP64 bound)
     if opt.get('exp_table', False) and not sp:
         out.append('#define KX_EXP_TABLE 1')
-    out.append('#include "kx_math.cuh"')
-    out.append(f'#define KX_N {N}')
     for d in opt.get('defines', ()):               # development switches (tools/build_variants.py)
         out.append(f'#define {d}')
+    out.append('#include "kx_math.cuh"')
+    out.append(f'#define KX_N {N}')
     out.append(f'#define KX_SINGLE_PRECISION {1 if sp else 0}')
     out.append('typedef float real;\ntypedef float2 real2;' if sp else 'typedef double real;\ntypedef double2 real2;')
     out.append('')
