@@ -254,12 +254,12 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     limit = 227 * 1024
     ns = -(-NP // 8) * 8                           # doubles reserved per state in tensor memory
     dchunk = tb * tb * 5
-    cmax0 = max(dchunk, tb * (wr + 6))             # at least one species block per Wilke / species chunk
+    cmax0 = max(dchunk, tb * (wr + 12))            # at least one species block per chunk of species rows
 
     def rows(width):
         return tb * min(NB, max(1, cmax0 // (tb * width)))
-    srows, vrows, urows = rows(12), rows(wr), rows(wr + 6)
-    cmax = -(-max(dchunk, srows * 12, vrows * wr, urows * (wr + 6)) // 2) * 2
+    vrows, urows = rows(wr + 12), rows(wr + 6)
+    cmax = -(-max(dchunk, vrows * (wr + 12), urows * (wr + 6)) // 2) * 2
     # (threads, states per thread) in order of measured preference: 8 warps before 4, two states per thread (half
     # the coefficient wavefronts per state) before one.  heptaneLu88 (88 species): 256 x 1 gives 236, 128 x 2 197 M
     # states/s; EtOHKonnov (129 species) only fits 128 x 1 (97 vs 72 M for the shared-memory kernel).
@@ -307,16 +307,14 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
         if k < N:
             return list(fits.conductivity[k]) + list(fits.viscosity[k]) + [M[k] ** -0.25, 0.0]
         return [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0.0]
-    for r0 in range(0, NP, srows):
-        add_chunk(v for k in range(r0, min(NP, r0 + srows)) for v in species_row(k))
     for r0 in range(0, NP, vrows):
         add_chunk(v for k in range(r0, min(NP, r0 + vrows))
-                  for v in (([float(x) for x in V[k]] if k < N else [0.0] * rank) + [0.0] * (wr - rank)))
+                  for v in (species_row(k) + ([float(x) for x in V[k]] if k < N else [0.0] * rank) + [0.0] * (wr - rank)))
     for r0 in range(0, NP, urows):
         add_chunk(v for k in range(r0, min(NP, r0 + urows))
                   for v in (([float(x) for x in U[k]] + [0.0] * (wr - rank) + list(fits.viscosity[k]) + [M[k] ** -0.25])
                             if k < N else [0.0] * wr + [1.0, 0, 0, 0, 0, 1.0]))
-    nsc, nvc, nuc = -(-NP // srows), -(-NP // vrows), -(-NP // urows)
+    nvc, nuc = -(-NP // vrows), -(-NP // urows)
     for kb in range(NB):
         for jb in range(kb + 1):
             tile = []
@@ -335,10 +333,8 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     out.append(f'#define KX_STAGES {stages}')
     out.append(f'#define KX_CHUNK_MAX {cmax}')
     out.append(f'#define KX_WR {wr}')
-    out.append(f'#define KX_SROWS {srows}')
     out.append(f'#define KX_VROWS {vrows}')
     out.append(f'#define KX_UROWS {urows}')
-    out.append(f'#define KX_NSC {nsc}')
     out.append(f'#define KX_NVC {nvc}')
     out.append(f'#define KX_NUC {nuc}')
     out.append(f'#define KX_N_CHUNKS {n_chunks}')
@@ -366,37 +362,6 @@ def wilke_low_rank(M, tol=1e-13):
         rank += 1
         U, V = u[:, :rank] * s[:rank], vt[:rank].T
     return U, V, rank
-
-
-def _wilke_chunks(M, N, NP, tb, wchunk):
-    """Wilke mass factors c_kj = 1/sqrt(8 (1 + M_k/M_j)), one chunk per k-block: [kb][j][i], k = kb*tb + i, j < NP."""
-    wil = []
-    for kb in range(NP // tb):
-        chunk = []
-        for j in range(NP):
-            for i in range(tb):
-                k = kb * tb + i
-                chunk.append(1.0 / math.sqrt(8.0 * (1.0 + M[k] / M[j])) if (k < N and j < N) else 0.0)
-        chunk += [0.0] * (wchunk - len(chunk))
-        wil += chunk
-    return wil
-
-
-def _diff_tiles(fits, N, NP, tb, dchunk):
-    """Binary diffusion quartics, lower-triangular tiles (kb >= jb), 5 coefficients + pad per pair; padded pairs
-    evaluate to D = 1."""
-    dif = []
-    for kb in range(NP // tb):
-        for jb in range(kb + 1):
-            for i in range(tb):
-                for j in range(tb):
-                    k, jj = kb * tb + i, jb * tb + j
-                    if k < N and jj < N and k > jj:
-                        dif += list(fits.diffusivity[k][jj]) + [0.0]
-                    else:
-                        dif += [1.0, 0.0, 0.0, 0.0, 0.0, 0.0]
-            dif += [0.0] * (dchunk - tb * tb * 6)
-    return dif
 
 
 def emit_module(mech, fits, options=None, single_precision=False):

@@ -16,17 +16,23 @@
 //     tcgen05.st / tcgen05.ld 32x32b, SASS STTM / LDTM), the X_k stay in shared memory as [k][state]: 8 warps
 //     of two-state threads per SM, and the S_k traffic (b_j in the Wilke sums, the read-modify-write of the
 //     column sums per tile) moves off the LSU pipe onto the otherwise unused TMEM datapath.
-//   * The table stream (Wilke k-blocks, then diffusion tiles) goes through a KX_STAGES-deep ring of TMA bulk
-//     copies with full/empty mbarriers (no CTA-wide barrier per chunk).
-//   * State rows are loaded in fully unrolled batches of 32 independent loads per state.
+//   * The Wilke sum uses a rank-KX_WR factorisation of its mass-factor matrix (see the Wilke section below):
+//     6 N r instead of 3 N^2 multiply-adds.
+//   * All tables (species quartics, Wilke factors, diffusion tiles) are ONE stream of chunks that goes through a
+//     KX_STAGES-deep ring of TMA bulk copies with full/empty mbarriers (no CTA-wide barrier per chunk, no
+//     constant-cache loads in the loops).
+//   * Persistent CTAs (one per SM) loop over batches of KX_BK2_BLOCK * KX_P states; tensor-memory allocation,
+//     barrier set-up and the ring's prefetch carry across batches.  KX_TEAMS = 2 splits the CTA into two
+//     independent half-CTA teams with skewed phases (measured slower: instruction-cache misses; off).
+//   * State rows are loaded in fully unrolled batches of 32 independent loads for all KX_P states.
 //
-// The including translation unit defines KX_N, KX_NP (multiple of KX_TB), KX_TB, KX_P, KX_BK2_BLOCK (threads;
-// a multiple of 128 so that the warps spread evenly over the four TMEM lane quadrants), KX_NS (doubles reserved
-// per state in TMEM, >= KX_NP), KX_STAGES, KX_CHUNK_MAX, KX_DCHUNK (= KX_TB^2 * 6), KX_WR (even: rank of the
-// Wilke factorisation), KX_WB (species blocks per Wilke chunk), KX_NWC (Wilke chunks per factor), KX_RCP_DIFF and
-//   __constant__ double kx_rcpM[KX_N], kx_M[KX_N], kx_m4[KX_N], kx_cond[KX_N][5], kx_visc[KX_N][5]
-//   __device__   double kx_wilke_v[KX_NP][KX_WR], kx_wilke_u[KX_NP][KX_WR]   c_kj = sum_q u[k][q] v[j][q]
-//   __device__   double kx_diff[n_tiles][KX_DCHUNK]  lower-triangular tiles, row-major over (kb, jb); 5 coefs + pad
+// The including translation unit defines KX_N, KX_NP (multiple of KX_TB), KX_TB, KX_P, KX_TEAMS, KX_BK2_BLOCK
+// (threads; KX_BK2_BLOCK / KX_TEAMS a multiple of 128 so that a team's warps cover the four TMEM lane quadrants),
+// KX_NS (doubles reserved per state in TMEM, >= KX_NP), KX_STAGES, KX_CHUNK_MAX (reals per stage), KX_WR (even:
+// rank of the Wilke factorisation), the chunk layout KX_N_CHUNKS / KX_NVC / KX_NUC / KX_VROWS / KX_UROWS (below), KX_RCP_DIFF and the tables
+//   __constant__ double kx_rcpM[KX_N], kx_M[KX_N]          1/M_k, M_k
+//   __constant__ int    kx_chunk_off[KX_N_CHUNKS + 1]      chunk boundaries in kx_bk2_stream (reals)
+//   __device__   double kx_bk2_stream[]                    the concatenated chunks, 16-byte aligned each
 #pragma once
 #include <cstdint>
 #include "kx_math.cuh"
@@ -53,8 +59,8 @@ KX_DEVICE real kx_quartic(const real* __restrict__ c, real l, real l2, real l4)
 }
 // The coefficient stream of one batch: KX_N_CHUNKS chunks of the concatenated table kx_bk2_stream, chunk c =
 // reals [kx_chunk_off[c], kx_chunk_off[c + 1]):
-//   KX_NSC chunks of the species table  (KX_SROWS rows x 12: conductivity quartic, viscosity quartic, M^-1/4, -)
-//   KX_NVC chunks of the Wilke factor V (KX_VROWS rows x KX_WR)
+//   KX_NVC chunks of species rows, first pass (KX_VROWS rows x (12 + KX_WR): conductivity quartic, viscosity
+//          quartic, M^-1/4, -, row of the Wilke factor V)
 //   KX_NUC chunks of the Wilke factor U (KX_UROWS rows x (KX_WR + 6): U row, viscosity quartic, M^-1/4)
 //   the lower-triangular diffusion tiles (KX_TB^2 pairs x 5 coefficients), row-major over (kb, jb <= kb)
 // Rows per chunk are multiples of KX_TB; padded species rows hold quartics = 1, M^-1/4 = 1, U = V = 0.
@@ -180,9 +186,9 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   // so with two teams one team's memory-bound prologue / epilogue overlaps the other's FP64 loops (the second
   // team starts half a batch late and the offset persists).
   constexpr int P = KX_P, TEAMS = KX_TEAMS, TT = KX_BK2_BLOCK / TEAMS, LDT = TT * P, TB = KX_TB;
-  constexpr int NWT = TT / 32, STG = KX_STAGES, R = KX_WR, RU = KX_WR + 6;
+  constexpr int NWT = TT / 32, STG = KX_STAGES, R = KX_WR, RU = KX_WR + 6, RV = KX_WR + 12;
   constexpr int N_CHUNKS = KX_N_CHUNKS;
-  constexpr int C_V = KX_NSC, C_U = C_V + KX_NVC, C_D = C_U + KX_NUC;   // first chunk of V, U, the tiles
+  constexpr int C_U = KX_NVC, C_D = C_U + KX_NUC;   // first chunk of U, of the tiles
   constexpr int TM_COLS = (KX_BK2_BLOCK / 128) * P * 2 * KX_NS;         // columns in use per TMEM lane
   static_assert((STG & (STG - 1)) == 0 && TT % 128 == 0 && TM_COLS <= 512 && KX_NS >= KX_NP, "shape");
   static_assert(C_D + KX_N_DTILES == N_CHUNKS, "chunk table");
@@ -319,81 +325,47 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #endif
     }
 
-    // ---- conductivity, and per-species viscosity factors b_k = 1/w_k (to tensor memory) ----
-    {
-      real s1[P], s2[P];
-#pragma unroll
-      for (int p = 0; p < P; p++) s1[p] = s2[p] = 0;
-#pragma unroll 1
-      for (int c = 0; c < KX_NSC; c++) {
-        const real* __restrict__ sr = acquire();
-        const int kb1 = min(KX_NB, (c + 1) * (KX_SROWS / TB));
-#pragma unroll 1
-        for (int kb = c * (KX_SROWS / TB); kb < kb1; kb++, sr += TB * 12) {
-          real b[P][TB];
-#pragma unroll
-          for (int i = 0; i < TB; i++) {
-            const int k = kb * TB + i;
-            const real* row = sr + i * 12;
-            const real m4 = row[10];
-#pragma unroll
-            for (int p = 0; p < P; p++) {
-              const real x = k < KX_N ? X[x_row(k) + p * TT] * Mbar[p] : (real)0;
-              if (k < KX_N) X[x_row(k) + p * TT] = x;
-              const real lam = kx_quartic(row, lnT[p], lnT2[p], lnT4[p]);
-              s1[p] = fma(x, lam, s1[p]);
-              s2[p] = fma(x, kx_rcp(lam), s2[p]);
-              b[p][i] = kx_rcp(kx_quartic(row + 5, lnT[p], lnT2[p], lnT4[p]) * m4);
-            }
-          }
-#pragma unroll
-          for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, kb * TB), b[p]);
-        }
-        release();
-      }
-#pragma unroll
-      for (int p = 0; p < P; p++)
-        if (live[p]) kx_st_stream(conductivity + id[p], (ST)(sqrT[p] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
-    }
-    kx_tm_wait_st();
-
     // ---- viscosity: Wilke, three matrix-vector products with a LOW-RANK mass-factor matrix ----
     //      (C1 + C2 v_k/v_j)^2 = c_kj (1 + w_k b_j)^2,  Phi_k = sum_j c_kj X_j (1 + 2 w_k b_j + w_k^2 b_j^2)
     //      c_kj = (8 (1 + M_k/M_j))^-1/2 is a smooth kernel in ln M_k - ln M_j: its numerical rank is KX_WR
     //      (12 for GRI-3.0, 14 for the 129-species EtOHKonnov), c = U V^T from an SVD at generation time.
     //      So  t_m = V^T (X b^m),  Phi_k = U_k . (t_0 + 2 w_k t_1 + w_k^2 t_2):  6 N r instead of 3 N^2 DFMA.
     {
-      real t0[P][R], t1[P][R], t2[P][R];
+      real t0[P][R], t1[P][R], t2[P][R], s1[P], s2[P];
 #pragma unroll
-      for (int p = 0; p < P; p++)
+      for (int p = 0; p < P; p++) {
+        s1[p] = s2[p] = 0;
 #pragma unroll
         for (int q = 0; q < R; q++) t0[p][q] = t1[p][q] = t2[p][q] = 0;
+      }
+      // first pass over the species (rows of [conductivity quartic, viscosity quartic, M^-1/4, -, V_j]): mole
+      // fraction X_j, the conductivity sums, b_j = 1/w_j and the three projections t_m -- b_j is used on the spot
 #pragma unroll 1
       for (int c = 0; c < KX_NVC; c++) {
         const real* __restrict__ cv = acquire();
         const int jb1 = min(KX_NB, (c + 1) * (KX_VROWS / TB));
 #pragma unroll 1
-        for (int jb = c * (KX_VROWS / TB); jb < jb1; jb++, cv += TB * R) {
-          unsigned raw[P][2 * TB];
-          real b[P][TB];
-#pragma unroll
-          for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, jb * TB), raw[p]);
-          kx_tm_wait_ld();
-#pragma unroll
-          for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], b[p]);
+        for (int jb = c * (KX_VROWS / TB); jb < jb1; jb++, cv += TB * RV) {
 #pragma unroll
           for (int jj = 0; jj < TB; jj++) {
             const int j = jb * TB + jj;
+            const real* row = cv + jj * RV;
+            const real m4 = row[10];
             real x[P], xb[P], xbb[P];
 #pragma unroll
             for (int p = 0; p < P; p++) {
-              x[p] = j < KX_N ? X[x_row(j) + p * TT] : (real)0;
-              xb[p] = x[p] * b[p][jj];
-              xbb[p] = xb[p] * b[p][jj];
+              x[p] = j < KX_N ? X[x_row(j) + p * TT] * Mbar[p] : (real)0;
+              if (j < KX_N) X[x_row(j) + p * TT] = x[p];
+              const real lam = kx_quartic(row, lnT[p], lnT2[p], lnT4[p]);
+              s1[p] = fma(x[p], lam, s1[p]);
+              s2[p] = fma(x[p], kx_rcp(lam), s2[p]);
+              const real b = kx_rcp(kx_quartic(row + 5, lnT[p], lnT2[p], lnT4[p]) * m4);
+              xb[p] = x[p] * b;
+              xbb[p] = xb[p] * b;
             }
 #pragma unroll
             for (int q = 0; q < R; q += 2) {
-              const real2 vv = *reinterpret_cast<const real2*>(cv + jj * R + q);
+              const real2 vv = *reinterpret_cast<const real2*>(row + 12 + q);
 #pragma unroll
               for (int p = 0; p < P; p++) {
                 t0[p][q] = fma(vv.x, x[p], t0[p][q]);
@@ -408,6 +380,9 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         }
         release();
       }
+#pragma unroll
+      for (int p = 0; p < P; p++)
+        if (live[p]) kx_st_stream(conductivity + id[p], (ST)(sqrT[p] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
 #pragma unroll
       for (int p = 0; p < P; p++)
 #pragma unroll

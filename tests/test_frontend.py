@@ -117,7 +117,7 @@ def test_bk2_kernel_plan():
     sizes = np.diff(offs)
     assert (sizes > 0).all() and (sizes % 2 == 0).all() and sizes.max() <= d['KX_CHUNK_MAX']
     n_tiles = (d['KX_NP'] // d['KX_TB']) * (d['KX_NP'] // d['KX_TB'] + 1) // 2
-    assert d['KX_NSC'] + d['KX_NVC'] + d['KX_NUC'] + n_tiles == d['KX_N_CHUNKS']
+    assert d['KX_NVC'] + d['KX_NUC'] + n_tiles == d['KX_N_CHUNKS']
     smem = int(re.search(r'per_cta = (\d+);.*\n  const size_t smem = (\d+);', src).group(2))
     assert smem <= 227 * 1024
     assert smem >= (d['KX_TEAMS'] * d['KX_STAGES'] * d['KX_CHUNK_MAX'] + 53 * 512) * 8
