@@ -110,10 +110,50 @@ class BK1Emitter:
         return f'{fn}({arg_expr})'
 
     def EG(self, k):
-        return f'gs[{self.eg_slot[k]} * {self.block}]' if self.gibbs_in_smem else f'eg{k}'
+        return self.val(self.eg_slot[k]) if self.gibbs_in_smem else f'eg{k}'
 
     def RG(self, k):
-        return f'gs[{self.rg_slot[k]} * {self.block}]' if self.gibbs_in_smem else f'rg{k}'
+        return self.val(self.rg_slot[k]) if self.gibbs_in_smem else f'rg{k}'
+
+    # ---- per-thread scratch slots: shared memory [slot][thread] or tensor memory (slot ids >= TM_BASE) --------
+    TM_BASE = 10000
+
+    def is_tm(self, slot):
+        return slot >= self.TM_BASE
+
+    def val(self, slot):
+        """rvalue of a slot: the shared-memory word itself, or the temporary a preceding fetch() has loaded"""
+        if self.is_tm(slot):
+            assert slot in self._fetched, 'tensor-memory slot read without fetch()'
+            return f'tv{slot - self.TM_BASE}'
+        return f'gs[{slot} * {self.block}]'
+
+    def store(self, slot, expr, indent=''):
+        if self.is_tm(slot):
+            self.w(f'{indent}kx_tm_st_d(tmb + {2 * (slot - self.TM_BASE)}, {expr});')
+            self._tm_dirty = True
+        else:
+            self.w(f'{indent}gs[{slot} * {self.block}] = {expr};')
+
+    def fetch(self, slots, indent=''):
+        """make the tensor-memory slots among `slots` readable inside the current C scope: batched tcgen05.ld,
+        one wait, values pinned behind the wait"""
+        tm = [t for t in dict.fromkeys(slots) if self.is_tm(t)]
+        self._fetched = set(tm)
+        if not tm:
+            return
+        w = self.w
+        if self._tm_dirty:
+            w(f'{indent}kx_tm_wait_st();')
+            self._tm_dirty = False
+        for t in tm:
+            j = t - self.TM_BASE
+            w(f'{indent}unsigned tl{j}, th{j}; kx_tm_ld_d(tmb + {2 * j}, tl{j}, th{j});')
+        w(f'{indent}kx_tm_wait_ld();')
+        for t in tm:
+            j = t - self.TM_BASE
+            w(f'{indent}const double tv{j} = kx_tm_pin(tl{j}, th{j});')
+        self.stats['tm_ld'] = self.stats.get('tm_ld', 0) + len(tm)
 
     # ---- thermo ------------------------------------------------------------------------------
     def nasa_select(self, k, make):
@@ -264,8 +304,13 @@ class BK1Emitter:
 
     # ---- main --------------------------------------------------------------------------------
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
-             reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False):
+             reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False,
+             tmem_slots=0, smem_cap=0, tmem_cols=512):
         """block / min_blocks: launch bounds.
+        tmem_slots: > 0: that many doubles per thread of TENSOR MEMORY hold scratch slots beside at most `smem_cap`
+          shared-memory slots (large mechanisms: EtOHKonnov needs 210 slots = 1.7 KB per thread, which limits a
+          shared-memory-only kernel to 4 warps per SM).  Third-body sums go to tensor memory first, exp(+-g_k) to
+          shared memory while it lasts.  The kernel then allocates all 512 TMEM columns (one CTA per SM).
         sync_every: a CTA-wide barrier every that many reactions keeps the warps of a CTA inside the same
           window of the straight-line code so instruction-cache fills are shared (0 = none).
         gibbs_in_smem: exp(+-g_k) of live species in shared memory slots [slot][thread] (slots are recycled
@@ -292,6 +337,8 @@ class BK1Emitter:
         self.ld1 = 'kx_ld_keep' if l1_keep else 'kx_ld_stream'
         self.ld2 = 'kx_ld_keep' if l1_keep else 'kx_ld_stream'
         self._flags = {}
+        self._tm_dirty, self._fetched = False, set()
+        self.tmem_slots = tmem_slots
         body = []
         self.lines = body
         w = self.w
@@ -360,17 +407,36 @@ class BK1Emitter:
         # shared-memory slot allocator ([slot][thread] doubles); the Y ring (if any) takes the first slots
         self.eg_slot, self.rg_slot = {}, {}
         free_slots, n_slots = [], (ring if ring else 0)
+        free_tm, n_tm = [], 0
 
-        def take_slot():
-            nonlocal n_slots
-            if free_slots:
-                return free_slots.pop(0)
-            n_slots += 1
-            return n_slots - 1
+        def take_slot(prefer_tm=False):
+            nonlocal n_slots, n_tm
+            for pool in (('t', 's') if prefer_tm else ('s', 't')):
+                if pool == 's':
+                    if free_slots:
+                        return free_slots.pop(0)
+                    if not tmem_slots or n_slots < smem_cap:
+                        n_slots += 1
+                        return n_slots - 1
+                elif tmem_slots:
+                    if free_tm:
+                        return free_tm.pop(0)
+                    if n_tm < tmem_slots:
+                        n_tm += 1
+                        return self.TM_BASE + n_tm - 1
+            raise RuntimeError(f'BK1 emitter: out of scratch slots ({smem_cap} shared + {tmem_slots} tensor memory)')
+
+        def release_slot(slot):
+            (free_tm if self.is_tm(slot) else free_slots).append(slot)
 
         if gibbs_in_smem or ring:
             w('extern __shared__ double kx_sm[];')
             w('double* const gs = kx_sm + threadIdx.x;')
+        if tmem_slots:
+            # this thread's tensor-memory columns: lane quadrant of the warp, column block of the warp group
+            w('__shared__ unsigned kx_tm_slot;')
+            w(f'const unsigned tm_alloc = kx_tm_alloc_all<{tmem_cols}>(&kx_tm_slot);')
+            w(f'const unsigned tmb = tm_alloc + (((threadIdx.x >> 5) & 3u) << 21) + (threadIdx.x >> 7) * {2 * tmem_slots}u;')
         w('#ifdef KX_EXP_TABLE')
         w('kx_exptab_init();')
         w('#endif')
@@ -381,9 +447,10 @@ class BK1Emitter:
         # third-body sums M_i (and ln M_i) are needed all along the reaction list: in shared memory they do not
         # occupy 2 registers each for the whole kernel (GRI-3.0: 10 + 5 values, EtOHKonnov: 30 + 15)
         eff_smem = bool(eff_in_smem and gibbs_in_smem)
-        eff_ref = {}
+        eff_slot = {}
         for name in eff_names.values():
-            eff_ref[name] = f'gs[{take_slot()} * {block}]' if eff_smem else name
+            if eff_smem:
+                eff_slot[name] = take_slot(prefer_tm=True)
         w('const double T = Tref * kx_ld_stream(state + id);')
         w('const double rcpT = kx_rcp(T);')
         w('const double lnT = kx_log(T);')
@@ -391,6 +458,28 @@ class BK1Emitter:
         if not eff_smem:
             for name in eff_names.values():
                 w(f'double {name};')
+
+        def collider(rx):
+            """name of the third-body concentration of a reaction: an efficiency-vector sum 'M<i>', a single
+            species 'cs<k>', or the total concentration 'Cm'"""
+            if rx.efficiencies is not None:
+                return eff_names[tuple(rx.efficiencies)]
+            if rx.third_body_index >= 0:
+                return f'cs{rx.third_body_index}'
+            return 'Cm'
+
+        # ln(M) once per distinct collider of a Troe reaction whose Pr is formed as exp(.)*M
+        # (guarded like the reference's log10(Pr + CFLOAT_MIN))
+        need_ln = []
+        for rx in m.reactions:
+            if rx.kind == 'Troe':
+                name = collider(rx)
+                arg, _ = self.ratio_expr(rx)
+                if not name.startswith('cs') and arg is not None and name not in need_ln:
+                    need_ln.append(name)
+        if not eff_smem:
+            for name in need_ln:
+                w(f'double ln_{name};')
         kept = set(k for k in first if first[k] <= keep_until) if keep_until else set()
         self.kept = kept
         if kept:
@@ -407,37 +496,48 @@ class BK1Emitter:
                     w(f'  a{name} = fma({K(vec[k] - 1)}, w{k}, a{name});')
         w('  rho = pR * rcpT * kx_rcp(rcpMbar);')
         w('  Cm = rho * rcpMbar;')
+        ln_slot, ln_collider = {}, {}
         for name in eff_names.values():
-            w(f'  {eff_ref[name]} = fma(rho, a{name}, Cm);')
+            if eff_smem:
+                w(f'  a{name} = fma(rho, a{name}, Cm);')
+                self.store(eff_slot[name], f'a{name}', '  ')
+            else:
+                w(f'  {name} = fma(rho, a{name}, Cm);')
+        for name in need_ln:
+            src = ('a' + name) if (eff_smem and name != 'Cm') else name
+            if eff_smem:
+                ln_slot[name] = take_slot(prefer_tm=True)
+                self.store(ln_slot[name], f'kx_log(fmax({src}, 1e-300))', '  ')
+            else:
+                ln_collider[name] = 'ln_' + name
+                w(f'  ln_{name} = kx_log(fmax({src}, 1e-300));')
+            self.stats['log'] += 1
         w('}')
         w(f'const double C0 = {K(const.ONE_ATM / const.R_GAS)} * rcpT;')
         w(f'const double rcpC0 = {K(const.R_GAS / const.ONE_ATM)} * T;')
         flag_pos = len(body)
 
-        def collider(rx):
-            if rx.efficiencies is not None:
-                return eff_ref[eff_names[tuple(rx.efficiencies)]]
-            if rx.third_body_index >= 0:
-                return f'cs{rx.third_body_index}'
-            return 'Cm'
+        def collider_slots(rx):
+            """scratch slots a reaction reads for its third body (value, ln value)"""
+            out = []
+            name = collider(rx)
+            if rx.kind in ('three-body', 'pressure-modification', 'Troe', 'SRI'):
+                if name in eff_slot:
+                    out.append(eff_slot[name])
+                if rx.kind == 'Troe' and name in ln_slot and self.ratio_expr(rx)[0] is not None:
+                    out.append(ln_slot[name])
+            return out
 
-        # ln(M) once per distinct collider of a Troe reaction whose Pr is formed as exp(.)*M
-        # (guarded like the reference's log10(Pr + CFLOAT_MIN))
-        ln_collider = {}
-        for rx in m.reactions:
-            if rx.kind == 'Troe':
-                name = collider(rx)
-                arg, _ = self.ratio_expr(rx)
-                if not name.startswith('cs'):
-                    if arg is not None and name not in ln_collider:
-                        if eff_smem:
-                            v = f'gs[{take_slot()} * {block}]'
-                            w(f'{v} = kx_log(fmax({name}, 1e-300));')
-                        else:
-                            v = 'ln_' + name
-                            w(f'const double {v} = kx_log(fmax({name}, 1e-300));')
-                        self.stats['log'] += 1
-                        ln_collider[name] = v
+        def collider_val(rx):
+            name = collider(rx)
+            return self.val(eff_slot[name]) if name in eff_slot else name
+
+        def ln_collider_val(rx):
+            """expression of ln(M) if it was precomputed for this reaction's collider, else None"""
+            name = collider(rx)
+            if name in ln_slot:
+                return self.val(ln_slot[name])
+            return ln_collider.get(name)
 
         # ---- per-species live state --------------------------------------------------------------
         used = sorted(first)                                  # species that occur in some reaction
@@ -506,14 +606,19 @@ class BK1Emitter:
             w('{')
             w(f'  const double g = fma(fma(fma(fma({c[5]}, T, {c[4]}), T, {c[3]}), T, {c[2]}), T, '
               f'fma({c[1]}, lnT, fma({c[6]}, rcpT, {c[0]})));')
+            def put(slots, name, expr):
+                if gibbs_in_smem:
+                    self.store(slots[k], expr, '  ')
+                else:
+                    w(f'  {name}{k} = {expr};')
             if need_pos[k]:
                 w(f'  const double e = {self.exp("g", glo, ghi)};')
-                w(f'  {self.EG(k)} = e;')
+                put(self.eg_slot, 'eg', 'e')
                 if need_neg[k]:
-                    w(f'  {self.RG(k)} = kx_rcp(e);')
+                    put(self.rg_slot, 'rg', 'kx_rcp(e)')
                     self.stats['rcp'] += 1
             else:
-                w(f'  {self.RG(k)} = {self.exp("-g", -ghi, -glo)};')
+                put(self.rg_slot, 'rg', self.exp("-g", -ghi, -glo))
             w('}')
 
         def retire(k, first_flush=True):
@@ -528,7 +633,7 @@ class BK1Emitter:
               f'fma({c[5]}, rcpT, {c[0]})), hsum);')
             for slots in (self.eg_slot, self.rg_slot):
                 if gibbs_in_smem and k in slots:
-                    free_slots.append(slots[k])
+                    release_slot(slots[k])
 
         def conc_product(nu):
             terms = []
@@ -585,6 +690,12 @@ class BK1Emitter:
                 rx = m.reactions[i]
                 w(f'  // {i + 1}: {rx.equation}')
                 w('  {')
+                if gibbs_in_smem:
+                    need = collider_slots(rx)
+                    if rx.reversible:
+                        need += [self.eg_slot[k] for k, v in enumerate(rx.nu_net) if v > 0]
+                        need += [self.rg_slot[k] for k, v in enumerate(rx.nu_net) if v < 0]
+                    self.fetch(need, '    ')
                 if rx.kind == 'P-log':
                     self._emit_plog(rx)
                 elif i == members[0]:
@@ -593,9 +704,9 @@ class BK1Emitter:
                     w(f'    double kf = kbase * {K(rx.rate.A / first_rx.rate.A)};')
 
                 if rx.kind == 'three-body':
-                    w(f'    kf *= {collider(rx)};')
+                    w(f'    kf *= {collider_val(rx)};')
                 elif rx.kind in ('pressure-modification', 'Troe', 'SRI'):
-                    M = collider(rx)
+                    M = collider_val(rx)
                     arg, rng = self.ratio_expr(rx)
                     if arg is not None:
                         w(f'    const double lnr = {arg};')
@@ -609,8 +720,8 @@ class BK1Emitter:
                     elif rx.kind == 'Troe':
                         # log10(Pr + CFLOAT_MIN): from the exponent and ln(M) when M is a sum of
                         # concentrations; literally when the collider is a single species (can be 0)
-                        if arg is not None and M in ln_collider:
-                            w(f'    const double logPr = (lnr + {ln_collider[M]}) * {K(1 / math.log(10))};')
+                        if arg is not None and ln_collider_val(rx) is not None:
+                            w(f'    const double logPr = (lnr + {ln_collider_val(rx)}) * {K(1 / math.log(10))};')
                         else:
                             w('    const double logPr = kx_log10(Pr + 1e-300);')
                             self.stats['log'] += 1
@@ -671,15 +782,18 @@ class BK1Emitter:
                 retire(k, first_flush=seg_index[(k, 'end', pos)] == 0)
                 live_now -= 1
         w(f'if (live) kx_st_stream(rates + id, {K(-const.R_GAS)} * T * hsum);')
+        if tmem_slots:
+            w(f'kx_tm_free_all<{tmem_cols}>(tm_alloc);')
 
         self.smem_doubles_per_thread = n_slots if (gibbs_in_smem or ring) else 0
-        self.schedule_stats.update(peak_live=peak_live, smem_slots=n_slots)
+        self.schedule_stats.update(peak_live=peak_live, smem_slots=n_slots, tmem_slots=n_tm)
         body[flag_pos:flag_pos] = ['  ' + v for v in self._flags.values()]
 
         head = [
             f'// BK1 (species production rates): {m.name}, {N} species / {m.n_reactions} reactions; '
             f'{self.stats["exp"]} kx_exp, {self.stats["exp_wide"]} wide exp, {self.stats["log"]} log, '
-            f'{self.stats["rcp"]} rcp per state; peak live species {peak_live}, {n_slots} smem slots',
+            f'{self.stats["rcp"]} rcp per state; peak live species {peak_live}, {n_slots} smem slots' +
+            (f', {n_tm} tensor-memory slots ({self.stats.get("tm_ld", 0)} loads)' if tmem_slots else ''),
             '// PF: per-state pressure field (extension); the reference flavour PF = false carries no trace of it',
             'template <bool PF>',
             f'__global__ void __launch_bounds__({block}, {min_blocks})',

@@ -384,13 +384,35 @@ def emit_module(mech, fits, options=None, single_precision=False):
             return e, e.emit('kx_bk1_f32', opt['block_bk1'], opt['minb_bk1'], 0, opt['reorder'])
         e = BK1Emitter(mech, K)
         src = e.emit('kx_bk1_f64', opt['block_bk1'], opt['minb_bk1'], opt['sync_every'], opt['gibbs_in_smem'],
-                     opt['reorder'], opt['prefetch'], opt['ring'], opt['pin_loads'], opt['l1_keep'], opt['keep_until'], opt['live_cap'], opt['eff_in_smem'], opt['nasa_indexed'])
+                     opt['reorder'], opt['prefetch'], opt['ring'], opt['pin_loads'], opt['l1_keep'], opt['keep_until'], opt['live_cap'], opt['eff_in_smem'], opt['nasa_indexed'],
+                     tmem_slots=bk1_tm['slots'], smem_cap=bk1_tm['smem_cap'], tmem_cols=bk1_tm.get('cols', 512))
         return e, src
 
+    bk1_tm = dict(slots=0, smem_cap=0)
     bk1, bk1_src = emit_bk1()
+    budget = 220 * 1024
+    # large mechanisms: when the scratch slots (exp(+-g_k) of live species, third-body sums) allow at most one
+    # 128-thread CTA per SM in shared memory (EtOHKonnov: 210 slots), spread them over shared AND tensor memory
+    # and run ONE 256-thread CTA per SM: twice the warps to hide latencies, and the (MB-sized) straight-line
+    # instruction stream is fetched once for 8 warps instead of 4.  'auto' | True | False
+    want_tm = opt.get('bk1_tmem', 'auto')
+    if not sp and opt['gibbs_in_smem'] and want_tm and not opt['ring']:
+        tm_block = opt.get('bk1_tmem_block', 256)
+        tm_ctas = opt.get('bk1_tmem_ctas', 1)            # CTAs per SM sharing the 512 columns
+        tm_cols = 512 // tm_ctas
+        tm_slots = tm_cols // 2 // (tm_block // 128)     # doubles per thread: the columns are shared by block/128 warp groups
+        cap = min(budget // (tm_block * tm_ctas * 8), opt.get('bk1_smem_cap', 1 << 30))
+        need = bk1.smem_doubles_per_thread
+        if (want_tm is True or need * 8 * 128 * 2 > budget) and need <= tm_slots + cap:
+            bk1_tm = dict(slots=tm_slots, smem_cap=cap, cols=tm_cols)
+            opt['block_bk1'], opt['minb_bk1'] = tm_block, tm_ctas
+            # the 8 warps share one pass over ~0.75 MB of straight-line code: a barrier every 4 reactions keeps
+            # them inside the same few KB of it (EtOHKonnov, M states/s: every 16: 118, 8: 135, 4: 157, 1: 148)
+            if 'sync_every' not in (options or {}):
+                opt['sync_every'] = 4
+            bk1, bk1_src = emit_bk1()
     # occupancy: the shared-memory slots per thread are a property of the schedule; if the requested CTAs per SM
     # do not fit, lower the CTA count (then the CTA size) and emit again
-    budget = 220 * 1024
     per_thread = bk1.smem_doubles_per_thread * 8
     changed = False
     while per_thread * opt['block_bk1'] * opt['minb_bk1'] > budget and (opt['minb_bk1'] > 1 or opt['block_bk1'] > 32):
@@ -414,6 +436,8 @@ def emit_module(mech, fits, options=None, single_precision=False):
     for d in opt.get('defines', ()):               # development switches (tools/build_variants.py)
         out.append(f'#define {d}')
     out.append('#include "kx_math.cuh"')
+    if bk1_tm['slots']:
+        out.append('#include "kx_tm.cuh"')
     out.append(f'#define KX_N {N}')
     out.append(f'#define KX_SINGLE_PRECISION {1 if sp else 0}')
     out.append('typedef float real;\ntypedef float2 real2;' if sp else 'typedef double real;\ntypedef double2 real2;')

@@ -37,6 +37,7 @@
 #include <cstdint>
 #include "kx_math.cuh"
 #include "kx_pipe.cuh"
+#include "kx_tm.cuh"
 
 #define KX_NB (KX_NP / KX_TB)
 // 1/D_kj in the pair loops: MUFU.RCP64H seed + ONE quadratic Newton step (2 FP64 instructions, relative error
@@ -116,8 +117,7 @@ KX_DEVICE void kx_tm_st16(unsigned taddr, const unsigned* r)
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-KX_DEVICE void kx_tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-KX_DEVICE void kx_tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// kx_tm_wait_ld() / kx_tm_wait_st(): kx_tm.cuh
 
 // issue the loads of N consecutive doubles (column `taddr`, 2 columns per double) in pieces of 8 / 4 / 2 / 1
 template <int N, int OFF = 0>

@@ -157,6 +157,30 @@ def test_bk2_kernel_variants_match_oracle(kinetix, variant):
     assert max(errs) <= TOL
 
 
+@pytest.mark.parametrize('variant', ['bk1_tm', 'bk1_tm_all', 'bk1_tm_2cta'])
+def test_bk1_tensor_memory_slots_match_oracle(kinetix, variant):
+    """BK1 with its per-thread scratch slots (exp(+-g_k), third-body sums) partly / entirely in tensor memory --
+    the layout large mechanisms get automatically (EtOHKonnov, test_largest_mechanism_etoh) -- forced on GRI-3.0:
+    one 256-thread CTA per SM with 512 TMEM columns, or two 128-thread CTAs with 256 columns each.  Ragged size:
+    the tail warps execute the warp-collective tcgen05.ld / st with clamped state indices."""
+    import __graft_entry__ as entry
+    lib = os.path.join(entry.variant_dir(variant), 'libkx_mech.so')
+    if not os.path.exists(lib):
+        pytest.skip(f'variant module {variant} not prebuilt')
+    kinetix.init(mech_path('gri30'), cache_dir=os.path.dirname(entry.variant_dir(variant)))
+    assert os.path.samefile(kinetix.modulePath(), lib)
+    N = kinetix.nSpecies()
+    kinetix.build(P_ATM, 1.0, [1.0 / N] * N, True)
+    orc = Oracle('gri30')
+    for S in (40 * 256 + 77, 5):
+        st = synthetic_states(N, S, seed=7)
+        new = _run_bk1(kinetix, st, 1.0)
+        ref = orc.production_rates(st, P_ATM)
+        rate_err, hrr_err = bk1_errors(new, ref)
+        print(f'{variant} S={S}: rates {rate_err:.3e} hrr {hrr_err:.3e}')
+        assert np.isfinite(new).all() and rate_err <= TOL and hrr_err <= TOL
+
+
 @pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
 def test_thermo_matches_oracle(kinetix, mech):
     N = _setup(kinetix, mech)
