@@ -410,6 +410,12 @@ def emit_module(mech, fits, options=None, single_precision=False):
             # them inside the same few KB of it (EtOHKonnov, M states/s: every 16: 118, 8: 135, 4: 157, 1: 148)
             if 'sync_every' not in (options or {}):
                 opt['sync_every'] = 4
+            # cap the live set (live-range splitting through the output rows, emit_bk1.py) so that the register
+            # spills shrink (EtOHKonnov: 87 -> 60 live species, 10-13 KB -> 6 KB of spill loads per state for 57
+            # more exp): without it the throughput falls with the batch size (158 M st/s at 1 Mi states, 127 M at
+            # 4 Mi: spill lines compete with the streamed rows for L2); with it 163 M at both sizes
+            if 'live_cap' not in (options or {}) and bk1.schedule_stats.get('peak_live', 0) > 60:
+                opt['live_cap'] = 60
             bk1, bk1_src = emit_bk1()
     # occupancy: the shared-memory slots per thread are a property of the schedule; if the requested CTAs per SM
     # do not fit, lower the CTA count (then the CTA size) and emit again
