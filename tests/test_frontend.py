@@ -83,6 +83,51 @@ def test_emitter_produces_a_module(name):
         assert f'  // {i + 1}: ' in src32
 
 
+def test_bk1_scratch_slot_plan():
+    """BK1 scratch slots (exp(+-g_k) of live species, third-body sums): small mechanisms keep them in shared memory
+    with several CTAs per SM; EtOHKonnov (210 slots) gets the shared + tensor memory layout -- one 256-thread CTA,
+    <= 110 shared-memory and <= 128 TMEM doubles per thread, live set capped -- and every TMEM value a reaction
+    reads is loaded (tcgen05.ld) inside that reaction's scope, behind a wait, before its first use."""
+    import re
+    src, stats = emit_module(mech('gri30'), None)
+    assert 'kx_tm_alloc_all' not in src and '__launch_bounds__(128, 3)' in src
+    assert stats['bk1_schedule']['tmem_slots'] == 0
+
+    src, stats = emit_module(mech('EtOHKonnov'), None)
+    sch = stats['bk1_schedule']
+    assert '__launch_bounds__(256, 1)' in src and 'kx_tm_alloc_all<512>' in src and 'kx_tm_free_all<512>' in src
+    assert 0 < sch['tmem_slots'] <= 128 and sch['smem_slots'] <= 110 and sch['peak_live'] <= 60
+    assert sch['smem_slots'] * 8 * 256 <= 227 * 1024
+    body = src[src.index('kx_bk1_f64('):src.index('kx_tm_free_all<512>')]
+    lines = body.split('\n')
+    for i, ln in enumerate(lines):
+        for t in re.findall(r'\btv(\d+)\b', ln):
+            if f'const double tv{t} = kx_tm_pin' in ln:
+                continue
+            # walk back to the definition: it must come before leaving the reaction's scope, after a wait
+            j = i
+            while f'const double tv{t} = kx_tm_pin(tl{t}, th{t});' not in lines[j]:
+                j -= 1
+                assert j > 0 and lines[j].strip() != '}', f'tv{t} used outside its fetch scope (line {i})'
+            assert any('kx_tm_wait_ld();' in lines[k] for k in range(max(0, j - 12), j))
+    # a TMEM store is followed by a wait::st before the next TMEM load
+    dirty = False
+    for ln in lines:
+        if 'kx_tm_st_d(' in ln:
+            dirty = True
+        elif 'kx_tm_wait_st();' in ln:
+            dirty = False
+        elif 'kx_tm_ld_d(' in ln:
+            assert not dirty, 'tcgen05.ld issued after a tcgen05.st without wait::st'
+    # forcing the layout with two CTAs per SM halves the columns each may allocate
+    src2, _ = emit_module(mech('gri30'), None, options={'bk1_tmem': True, 'bk1_tmem_block': 128, 'bk1_tmem_ctas': 2})
+    assert 'kx_tm_alloc_all<256>' in src2 and '__launch_bounds__(128, 2)' in src2
+    # a shape whose shared + tensor memory cannot hold the slots falls back to the shared-memory layout
+    src3, _ = emit_module(mech('gri30'), None, options={'bk1_tmem': True, 'bk1_smem_cap': 0, 'bk1_tmem_block': 512,
+                                                        'bk1_tmem_ctas': 2})
+    assert 'kx_tm_alloc_all' not in src3
+
+
 @pytest.mark.parametrize('name', ALL)
 def test_wilke_mass_factor_matrix_is_low_rank(name):
     """c_kj = (8 (1 + M_k/M_j))^-1/2 (reference mix_transport.py:311-317, 534-553) is a smooth kernel in
