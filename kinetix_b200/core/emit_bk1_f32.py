@@ -35,6 +35,11 @@ class FloatPool(ConstPool):
         v = float(v)
         if math.isinf(v) or abs(v) > 3.0e38:
             raise SystemExit(f'FP32 emitter: constant {v} does not fit single precision')
+        if self.inline:
+            # a 32-bit literal is an immediate operand or ONE MOV; a pool entry that is the second constant of an
+            # FFMA costs an LDC through the MIO queue (ncu: 40 % of the FP32 kernel's stall samples sat on LDC)
+            lit = _lit(v)
+            return f'({lit}f)' if ('e' in lit or '.' in lit or 'n' in lit) else f'({lit}.f)'
         return super().__call__(v)
 
     def definition(self, ctype='float'):
@@ -72,9 +77,12 @@ class BK1EmitterF32(BK1Emitter):
             return expr
         return K(math.log2(A0 / A_inf))
 
-    def emit(self, kernel_name='kx_bk1_f32', block=128, min_blocks=4, sync_every=0, reorder=True, **_):
+    def emit(self, kernel_name='kx_bk1_f32', block=128, min_blocks=4, sync_every=0, reorder=True, nasa_indexed=False, **_):
+        """nasa_indexed: False = every NASA-7 coefficient is a select between its two range values (immediates);
+        'ldg' = one load from a range-indexed float table through L1 (as in the FP64 emitter)."""
         m, N, K = self.m, self.N, self.K
         self._flags = {}
+        self.nasa_indexed, self.nasa_lo_tab, self.nasa_hi_tab = nasa_indexed, [], []
         body = []
         self.lines = body
         w = self.w
@@ -294,6 +302,20 @@ class BK1EmitterF32(BK1Emitter):
             '  }',
         ]
         return '\n'.join(head + body + ['}', ''])
+
+    def tmid_offset(self, tmid):
+        name = 'noff_' + repr(float(tmid)).replace('.', '_').replace('-', 'm')
+        if name not in self._flags:
+            self._flags[name] = f'const int {name} = (T <= {_lit(float(tmid))}f) ? 0 : KX_NASA_HALF;'
+        return name
+
+    def nasa_table_definition(self):
+        if not self.nasa_indexed:
+            return ''
+        vals = self.nasa_lo_tab + self.nasa_hi_tab
+        body = ',\n  '.join(', '.join(f'{float(v)!r}f' for v in vals[i:i + 6]) for i in range(0, len(vals), 6))
+        return (f'#define KX_NASA_HALF {len(self.nasa_lo_tab)}\n#define KX_NASA_LEN {len(vals)}\n'
+                f'__device__ const __align__(16) float kx_nasa_tab[{len(vals)}] = {{\n  {body}\n}};\n')
 
     def tmid_flag(self, tmid):
         name = 'lo_' + repr(float(tmid)).replace('.', '_').replace('-', 'm')

@@ -374,14 +374,16 @@ def emit_module(mech, fits, options=None, single_precision=False):
                block_bk2=128, minb_bk2=2, bk2_scratch=False, bk2_split=2)
     opt.update(options or {})
     N = mech.n_species
-    K = FloatPool('kcf') if sp else ConstPool('kc', inline=opt['inline_constants'], as_param=opt['param_constants'])
-    if sp:
-        opt['minb_bk1'] = max(opt['minb_bk1'], 4) if 'minb_bk1' not in (options or {}) else opt['minb_bk1']
+    K = FloatPool('kcf', inline=opt.get('inline_constants_f32', True)) if sp else ConstPool('kc', inline=opt['inline_constants'], as_param=opt['param_constants'])
+    # FP32 BK1 (GRI-3.0 fpmix, M states/s): constants as 32-bit immediates instead of pool loads 1800 -> 2640 (40 % of the
+    # stall samples sat on LDC: the second constant of an FFMA is an explicit load through the MIO queue), then
+    # 3 CTAs x 168 registers instead of 4 x 128: 2800; NASA table through L1 2580, barriers 2760-2810, 2 CTAs 1930
 
     def emit_bk1():
         if sp:
             e = BK1EmitterF32(mech, K)
-            return e, e.emit('kx_bk1_f32', opt['block_bk1'], opt['minb_bk1'], 0, opt['reorder'])
+            return e, e.emit('kx_bk1_f32', opt['block_bk1'], opt['minb_bk1'], opt.get('sync_every_f32', 0), opt['reorder'],
+                             nasa_indexed=opt.get('nasa_indexed_f32', False))
         e = BK1Emitter(mech, K)
         src = e.emit('kx_bk1_f64', opt['block_bk1'], opt['minb_bk1'], opt['sync_every'], opt['gibbs_in_smem'],
                      opt['reorder'], opt['prefetch'], opt['ring'], opt['pin_loads'], opt['l1_keep'], opt['keep_until'], opt['live_cap'], opt['eff_in_smem'], opt['nasa_indexed'],

@@ -13,8 +13,11 @@ sys.path.insert(0, ROOT)
 def one(args):
     name, mech, opts = args
     from kinetix_b200 import jit
-    out = os.path.join(ROOT, 'build', 'variants', name, mech)
-    jit.ensure_module(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech + '.yaml'), out, emit_options=opts)
+    opts = dict(opts)
+    sp = bool(opts.pop('_sp', False))          # "_sp": true builds the --single-precision module (<mech>-sp)
+    out = os.path.join(ROOT, 'build', 'variants', name, mech + ('-sp' if sp else ''))
+    jit.ensure_module(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech + '.yaml'), out, emit_options=opts,
+                      single_precision=sp)
     log = open(os.path.join(out, 'ptxas.log')).read()
     return name, [l.strip() for l in log.splitlines() if 'registers' in l or 'spill' in l]
 
