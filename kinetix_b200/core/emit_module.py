@@ -392,6 +392,16 @@ def emit_module(mech, fits, options=None, single_precision=False):
 
     bk1_tm = dict(slots=0, smem_cap=0)
     bk1, bk1_src = emit_bk1()
+    # small mechanisms: few live species need few registers, more resident CTAs pay (M states/s, 8 Mi states;
+    # FP64 3 -> 4 CTAs: LiDryer 13580 -> 13750, H2_Konnov 5470 -> 5980, gri30-20 3090 -> 3580; FP32 math 3 -> 6 / 8:
+    # LiDryer 29100 -> 34100 / 35600 = 5.7 TB/s of HBM traffic, H2_Konnov 14660 -> 16880 / 16160, gri30-20 9200 -> 10170 / 9140)
+    if 'minb_bk1' not in (options or {}) and 'block_bk1' not in (options or {}):
+        peak = bk1.schedule_stats.get('peak_live', N)
+        small = 4 if not sp else (8 if peak <= 8 else 6)
+        # FP64, 17-25 live species: chempolimi_edit (21) 1180 -> 1340, gri30-27 (19) and gri30-35 (25) unchanged
+        if peak <= (21 if not sp else 16) and small != opt['minb_bk1']:
+            opt['minb_bk1'] = small
+            bk1, bk1_src = emit_bk1()
     budget = 220 * 1024
     # large mechanisms: when the scratch slots (exp(+-g_k) of live species, third-body sums) allow at most one
     # 128-thread CTA per SM in shared memory (EtOHKonnov: 210 slots), spread them over shared AND tensor memory
