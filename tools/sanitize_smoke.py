@@ -10,8 +10,12 @@ sys.path.insert(0, ROOT)
 import kinetix_b200.host as kinetix  # noqa: E402
 from oracle.port import synthetic_states  # noqa: E402
 
-# gri30 / heptaneLu88: tensor-memory BK2 kernel (256 / 128 threads); LiDryer: one-state-per-thread kernel; sp: FP32
-for mech, sp in (('gri30', False), ('heptaneLu88', False), ('LiDryer', False), ('LiDryer', True)):
+# gri30 / heptaneLu88: tensor-memory BK2 kernel (256 / 128 threads); LiDryer: one-state-per-thread kernel; sp: FP32;
+# EtOHKonnov: BK1 with scratch slots in shared + tensor memory (256-thread CTA)
+MECHS = (('gri30', False), ('heptaneLu88', False), ('LiDryer', False), ('LiDryer', True), ('EtOHKonnov', False))
+if len(sys.argv) > 1:
+    MECHS = tuple((m, False) for m in sys.argv[1:])
+for mech, sp in MECHS:
     kinetix.init(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech + '.yaml'), single_precision=sp)
     N = kinetix.nSpecies()
     kinetix.build(101325.0, 1.0, [1.0 / N] * N, True)
