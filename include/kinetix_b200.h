@@ -60,6 +60,17 @@ int kx_init(const char* yaml_path, const kx_options* options);
  * first in kinetix.cpp:290-296,655-699).  kx_init does this implicitly. */
 int kx_prepare(const char* yaml_path, const kx_options* options);
 
+/* Extension hook = the reference's kinetixBuildKernel_t (kinetix.hpp:11-13, installed by init's optional
+ * `buildKernel` argument, kinetix.cpp:499-502,542): a host application may supply its own builder for the
+ * mechanism module.  When a builder is set, kx_init / kx_prepare call it INSTEAD of running the built-in
+ * generator + nvcc whenever the module is not in the cache (or KINETIX_B200_REBUILD is set): it must leave
+ * `<output_dir>/libkx_mech.so` (exporting the kxm_* interface) for (yaml_path, options) and return 0; any other
+ * return value makes the caller fail with that code in the message.  `user` is passed through.  The builder is a
+ * process-wide setting that survives kx_finalize; kx_set_module_builder(NULL, NULL) restores the default. */
+typedef int (*kx_build_module_fn)(const char* yaml_path, const kx_options* options, const char* output_dir,
+                                  void* user);
+int kx_set_module_builder(kx_build_module_fn builder, void* user);
+
 /* kinetix::isInitialized (kinetix.hpp:15).  Like the reference it becomes true after kx_build. */
 int kx_is_initialized(void);
 

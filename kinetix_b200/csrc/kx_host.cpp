@@ -117,6 +117,10 @@ bool resolve(F& f, const char* sym)
   return f != nullptr;
 }
 
+// host-supplied module builder (kx_set_module_builder); process-wide like the reference's static `buildKernel`
+kx_build_module_fn g_builder = nullptr;
+void* g_builder_user = nullptr;
+
 // Locate the compiled module of (mechanism, options) in the cache, generating + compiling it first if it
 // is missing (cf. kinetix.cpp:655-699: generator through system(), cached by option hash).  No CUDA calls.
 int prepare_module(const char* yaml_path, const kx_options& opt, std::string& lib)
@@ -131,7 +135,12 @@ int prepare_module(const char* yaml_path, const kx_options& opt, std::string& li
   const std::string dir = cache + "/" + tag;
   lib = dir + "/libkx_mech.so";
 
-  if (!exists(lib) || getenv("KINETIX_B200_REBUILD")) {
+  if ((!exists(lib) || getenv("KINETIX_B200_REBUILD")) && g_builder) {
+    if (opt.verbose) fprintf(stderr, "[kinetix_b200] module builder hook -> %s\n", dir.c_str());
+    const int rc = g_builder(yaml_path, &opt, dir.c_str(), g_builder_user);
+    if (rc != 0) return fail("kx_init: the module builder hook returned " + std::to_string(rc) + " for " + dir);
+    if (!exists(lib)) return fail("kx_init: the module builder hook did not produce " + lib);
+  } else if (!exists(lib) || getenv("KINETIX_B200_REBUILD")) {
     const char* py = getenv("KINETIX_B200_PYTHON") ? getenv("KINETIX_B200_PYTHON") : "python3";
     std::string parent = pkg.substr(0, pkg.find_last_of('/'));
     std::ostringstream cmd;
@@ -239,6 +248,13 @@ int kx_prepare(const char* yaml_path, const kx_options* opt_in)
   if (!exists(yaml_path)) return fail(std::string("kx_prepare: mechanism file not found: ") + yaml_path);
   std::string lib;
   return prepare_module(yaml_path, opt, lib);
+}
+
+int kx_set_module_builder(kx_build_module_fn builder, void* user)
+{
+  g_builder = builder;
+  g_builder_user = builder ? user : nullptr;
+  return 0;
 }
 
 int kx_is_initialized(void) { return g.built ? 1 : 0; }

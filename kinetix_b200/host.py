@@ -16,6 +16,7 @@ the library's message.  There is no CPU fallback: without the compiled CUDA libr
 """
 import ctypes
 import os
+import sys
 
 from . import jit
 
@@ -115,6 +116,47 @@ def init(yamlPath, device_id=0, tool='KinetiX', blockSize=0, single_precision=Fa
                  fit_rcp_diff_coeffs=int(fit_rcpDiffCoeffs), verbose=int(verbose),
                  cache_dir=cache_dir.encode() if cache_dir else None, tool=tool.encode() if tool else None)
     _check(library().kx_init(os.fspath(yamlPath).encode(), ctypes.byref(o)), 'kinetix.init')
+
+
+_BUILD_MODULE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(_Options), ctypes.c_char_p, ctypes.c_void_p)
+_builder_ref = None          # keeps the ctypes trampoline alive while it is installed
+
+
+def setBuildKernel(builder):
+    """Install a host-supplied module builder -- the counterpart of init's optional `buildKernel` argument
+    (kinetix.hpp:11-13, kinetix.cpp:499-502,542).  `builder(yaml_path: str, options: dict, output_dir: str) -> int`
+    is called by init / prepare instead of the built-in generator when the module is not cached; it must leave
+    `output_dir/libkx_mech.so` and return 0.  None restores the default."""
+    global _builder_ref
+    lib = library()
+    lib.kx_set_module_builder.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    if builder is None:
+        lib.kx_set_module_builder(None, None)
+        _builder_ref = None
+        return
+
+    def trampoline(yaml_path, opt, output_dir, _user):
+        try:
+            o = opt.contents
+            options = {name: getattr(o, name) for name, _ in _Options._fields_ if name not in ('cache_dir', 'tool')}
+            return int(builder(yaml_path.decode(), options, output_dir.decode()) or 0)
+        except Exception as e:          # never let an exception cross the C boundary
+            sys.stderr.write(f'[kinetix_b200] module builder raised: {e!r}\n')
+            return -1
+    ref = _BUILD_MODULE_FN(trampoline)
+    lib.kx_set_module_builder(ctypes.cast(ref, ctypes.c_void_p), None)
+    _builder_ref = ref
+
+
+def prepare(yamlPath, single_precision=False, fit_rcpDiffCoeffs=False, blockSize=0, cache_dir=None, verbose=False):
+    """kx_prepare: generate + compile the module into the cache without touching CUDA (what rank 0 does before
+    the other ranks start, kinetix.cpp:290-296,655-699)."""
+    o = _Options(block_size=blockSize, single_precision=int(single_precision),
+                 fit_rcp_diff_coeffs=int(fit_rcpDiffCoeffs), verbose=int(verbose),
+                 cache_dir=cache_dir.encode() if cache_dir else None)
+    lib = library()
+    lib.kx_prepare.argtypes = [ctypes.c_char_p, ctypes.POINTER(_Options)]
+    _check(lib.kx_prepare(os.fspath(yamlPath).encode(), ctypes.byref(o)), 'kinetix.prepare')
 
 
 def build(refPressure, refTemperature, refMassFractions, transport=True):

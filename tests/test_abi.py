@@ -56,6 +56,48 @@ def test_generated_module_exports_interface():
     assert abs(M[names.index('H2')] - 2.016e-3) < 1e-12
 
 
+def test_module_builder_hook(tmp_path):
+    """kx_set_module_builder = the reference's kinetixBuildKernel_t hook (kinetix.hpp:11-13): a host-supplied builder
+    replaces the built-in generator run when the module is not cached; its failures surface as errors; NULL restores
+    the default.  kx_prepare only (no CUDA)."""
+    import shutil
+    import kinetix_b200.host as kinetix
+    calls = []
+    prebuilt = jit.ensure_module(mech_path('LiDryer'))
+
+    def failing(yaml_path, options, output_dir):
+        calls.append((yaml_path, options['single_precision'], output_dir))
+        return 7
+
+    def copying(yaml_path, options, output_dir):        # an application shipping ahead-of-time compiled modules
+        calls.append((yaml_path, options['single_precision'], output_dir))
+        os.makedirs(output_dir, exist_ok=True)
+        shutil.copy(os.path.join(prebuilt, 'libkx_mech.so'), os.path.join(output_dir, 'libkx_mech.so'))
+        return 0
+
+    def lazy(yaml_path, options, output_dir):
+        return 0                                        # claims success without producing the module
+
+    try:
+        kinetix.setBuildKernel(failing)
+        with pytest.raises(kinetix.KinetixError) as e:
+            kinetix.prepare(mech_path('LiDryer'), cache_dir=str(tmp_path))
+        assert 'module builder hook returned 7' in str(e.value)
+        assert calls and calls[-1][0].endswith('LiDryer.yaml') and calls[-1][2] == str(tmp_path / 'LiDryer')
+        kinetix.setBuildKernel(lazy)
+        with pytest.raises(kinetix.KinetixError) as e:
+            kinetix.prepare(mech_path('LiDryer'), cache_dir=str(tmp_path))
+        assert 'did not produce' in str(e.value)
+        kinetix.setBuildKernel(copying)
+        kinetix.prepare(mech_path('LiDryer'), cache_dir=str(tmp_path))
+        assert os.path.exists(tmp_path / 'LiDryer' / 'libkx_mech.so')
+        n = len(calls)
+        kinetix.prepare(mech_path('LiDryer'), cache_dir=str(tmp_path))      # cached now: the hook is not called again
+        assert len(calls) == n
+    finally:
+        kinetix.setBuildKernel(None)
+
+
 def test_product_does_not_import_the_oracle():
     """the oracle is test infrastructure: nothing under kinetix_b200/ may reference it"""
     for dirpath, _, files in os.walk(os.path.join(ROOT, 'kinetix_b200')):
