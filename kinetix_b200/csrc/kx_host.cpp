@@ -407,6 +407,15 @@ int ensure_staging(size_t in_bytes, size_t out_bytes)
   return 0;
 }
 
+// error exit of a pipelined call: wait for the chunks already in flight (they read and write the CALLER's host
+// buffers, which the caller may release as soon as the call has returned), then pass the status on
+int drain(int status)
+{
+  for (int s = 0; s < State::SLOTS; s++)
+    if (g.streams[s]) cudaStreamSynchronize(g.streams[s]);
+  return status;
+}
+
 // copy rows [T; Y_0..Y_{N-1}] of `len` states starting at state s0 into a dense (N+1) x len device slab
 cudaError_t upload_chunk(const double* h_state, int64_t s0, int64_t len, int64_t offsetT, int64_t offset,
                          double* d, cudaStream_t st)
@@ -437,13 +446,13 @@ int kx_production_rates_host(int64_t n_states, int64_t offsetT, int64_t offset, 
     double* din = (double*)g.d_in[slot];
     double* dout = (double*)g.d_out[slot];
     cudaError_t e = upload_chunk(h_state, s0, len, offsetT, offset, din, st);
-    if (e != cudaSuccess) return cuda_fail("kx_production_rates_host: H2D", e);
-    if (int r = kx_production_rates(len, len, len, pressure, din, dout, KX_DTYPE_F64, st)) return r;
+    if (e != cudaSuccess) return drain(cuda_fail("kx_production_rates_host: H2D", e));
+    if (int r = kx_production_rates(len, len, len, pressure, din, dout, KX_DTYPE_F64, st)) return drain(r);
     e = cudaMemcpyAsync(h_rates + s0, dout, len * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
       e = cudaMemcpy2DAsync(h_rates + s0 + offsetT, offset * sizeof(double), dout + len, len * sizeof(double),
                             len * sizeof(double), N, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return cuda_fail("kx_production_rates_host: D2H", e);
+    if (e != cudaSuccess) return drain(cuda_fail("kx_production_rates_host: D2H", e));
   }
   for (int s = 0; s < State::SLOTS; s++) {
     cudaError_t e = cudaStreamSynchronize(g.streams[s]);
@@ -471,17 +480,17 @@ int kx_mixture_avg_transport_props_host(int64_t n_states, int64_t offsetT, int64
     double* din = (double*)g.d_in[slot];
     double* dout = (double*)g.d_out[slot];   // [viscosity | conductivity | rhoD rows]
     cudaError_t e = upload_chunk(h_state, s0, len, offsetT, offset, din, st);
-    if (e != cudaSuccess) return cuda_fail("kx_mixture_avg_transport_props_host: H2D", e);
+    if (e != cudaSuccess) return drain(cuda_fail("kx_mixture_avg_transport_props_host: H2D", e));
     if (int r = kx_mixture_avg_transport_props(len, len, len, pressure, din, dout, dout + len, dout + 2 * len,
                                                KX_DTYPE_F64, st))
-      return r;
+      return drain(r);
     e = cudaMemcpyAsync(h_viscosity + s0, dout, len * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(h_conductivity + s0, dout + len, len * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
       e = cudaMemcpy2DAsync(h_rho_d + s0, offset * sizeof(double), dout + 2 * len, len * sizeof(double),
                             len * sizeof(double), N, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return cuda_fail("kx_mixture_avg_transport_props_host: D2H", e);
+    if (e != cudaSuccess) return drain(cuda_fail("kx_mixture_avg_transport_props_host: D2H", e));
   }
   for (int s = 0; s < State::SLOTS; s++) {
     cudaError_t e = cudaStreamSynchronize(g.streams[s]);
@@ -512,11 +521,11 @@ int kx_rates_and_transport_host(int64_t n_states, int64_t offsetT, int64_t offse
     double* drates = (double*)g.d_out[slot];                 // (N+1) x len
     double* dtr = drates + (size_t)(N + 1) * len;            // [viscosity | conductivity | rhoD rows]
     cudaError_t e = upload_chunk(h_state, s0, len, offsetT, offset, din, st);
-    if (e != cudaSuccess) return cuda_fail("kx_rates_and_transport_host: H2D", e);
-    if (int r = kx_production_rates(len, len, len, pressure, din, drates, KX_DTYPE_F64, st)) return r;
+    if (e != cudaSuccess) return drain(cuda_fail("kx_rates_and_transport_host: H2D", e));
+    if (int r = kx_production_rates(len, len, len, pressure, din, drates, KX_DTYPE_F64, st)) return drain(r);
     if (int r = kx_mixture_avg_transport_props(len, len, len, pressure, din, dtr, dtr + len, dtr + 2 * len,
                                                KX_DTYPE_F64, st))
-      return r;
+      return drain(r);
     e = cudaMemcpyAsync(h_rates + s0, drates, len * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
       e = cudaMemcpy2DAsync(h_rates + s0 + offsetT, offset * sizeof(double), drates + len, len * sizeof(double),
@@ -528,7 +537,7 @@ int kx_rates_and_transport_host(int64_t n_states, int64_t offsetT, int64_t offse
     if (e == cudaSuccess)
       e = cudaMemcpy2DAsync(h_rho_d + s0, offset * sizeof(double), dtr + 2 * len, len * sizeof(double),
                             len * sizeof(double), N, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return cuda_fail("kx_rates_and_transport_host: D2H", e);
+    if (e != cudaSuccess) return drain(cuda_fail("kx_rates_and_transport_host: D2H", e));
   }
   for (int s = 0; s < State::SLOTS; s++) {
     cudaError_t e = cudaStreamSynchronize(g.streams[s]);
