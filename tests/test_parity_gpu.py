@@ -157,6 +157,26 @@ def test_bk2_kernel_variants_match_oracle(kinetix, variant):
     assert max(errs) <= TOL
 
 
+def test_etoh_large_batch_is_replication_invariant(kinetix):
+    """size-independent property at a many-wave size for the large-mechanism BK1 layout (scratch slots in shared +
+    tensor memory, live set capped with partial rates flushed to / accumulated in the output rows): a batch made of
+    320 copies of 1024 states (> 8 full waves of one 256-thread CTA per SM) must give 320 bit-identical copies of the
+    1024 results, every row written, and the first copy must match the oracle."""
+    mech = 'EtOHKonnov'
+    N = _setup(kinetix, mech)
+    base = synthetic_states(N, 1024, seed=5)
+    reps = 320
+    st = np.ascontiguousarray(np.tile(base, (1, reps)))
+    new = _run_bk1(kinetix, st, 1.0)
+    assert np.isfinite(new).all()
+    blocks = new.reshape(N + 1, reps, 1024)
+    assert (blocks == blocks[:, :1, :]).all()
+    ref = Oracle(mech, prefer_ref=False).production_rates(base, P_ATM)
+    rate_err, hrr_err = bk1_errors(np.ascontiguousarray(blocks[:, 0, :]), ref)
+    print(f'{mech} {st.shape[1]} states: replicas identical; first copy vs port: rates {rate_err:.3e} hrr {hrr_err:.3e}')
+    assert rate_err <= TOL and hrr_err <= TOL
+
+
 @pytest.mark.parametrize('variant', ['bk1_tm', 'bk1_tm_all', 'bk1_tm_2cta'])
 def test_bk1_tensor_memory_slots_match_oracle(kinetix, variant):
     """BK1 with its per-thread scratch slots (exp(+-g_k), third-body sums) partly / entirely in tensor memory --
