@@ -1,0 +1,78 @@
+"""CPU parity of the GENERATED BK1 kernel text: tests/emu executes the emitter's output thread by thread on the host
+(CUDA keywords, tensor memory and the few inline-PTX statements replaced by their C meaning; exp / log / reciprocal
+are the product's own code) and compares with the oracle at the 1e-10 bound.  This checks, without a GPU, what the
+emitter decides: reaction schedule, activation / retirement, slot recycling in shared and tensor memory, live-range
+splitting through the output rows, P-log branches, per-state pressure.  It is test infrastructure, not a CPU path
+of the product (the GPU tests in test_parity_gpu.py remain the parity tests proper)."""
+import numpy as np
+import pytest
+
+from oracle.port import synthetic_states
+from tests.common import Oracle, bk1_errors
+from tests.emu.emulate import BK1Emulator
+
+TOL = 1e-10
+P_ATM = 101325.0
+
+
+def _check(emu, orc, st, p, label):
+    new = emu.production_rates(st, p)
+    ref = orc.production_rates(st, p)
+    assert np.isfinite(new).all(), f'{label}: a scratch slot was read before it was written, or a row was not stored'
+    rate_err, hrr_err = bk1_errors(new, ref)
+    print(f'{label}: emulated kernel vs {orc.kind}: rates {rate_err:.2e} hrr {hrr_err:.2e}')
+    assert rate_err <= TOL and hrr_err <= TOL
+    return new
+
+
+@pytest.mark.parametrize('mech,prefer_ref', [('LiDryer', True), ('gri30', True), ('H2_Konnov', False)])
+def test_generated_bk1_on_cpu(mech, prefer_ref):
+    emu = BK1Emulator(mech)
+    st = synthetic_states(emu.mech.n_species, 300, seed=11)       # ragged: tail threads re-run the last state
+    _check(emu, Oracle(mech, prefer_ref=prefer_ref), st, P_ATM, mech)
+
+
+def test_generated_bk1_plog_and_pressure_field_on_cpu():
+    """chempolimi_edit: P-log reactions below / inside / above their pressure tables, then the same three pressures
+    as ONE launch with a per-state pressure field (the PF = true kernel)."""
+    mech = 'chempolimi_edit'
+    emu = BK1Emulator(mech)
+    orc = Oracle(mech)
+    N = emu.mech.n_species
+    st = synthetic_states(N, 90, seed=5)
+    pressures = (1013.25, 5.0e5, 2.0e7)
+    per_p = [_check(emu, orc, st, p, f'{mech} p={p:g}') for p in pressures]
+    field = np.repeat(np.array(pressures) / P_ATM, 90)
+    got = emu.production_rates(np.tile(st, (1, 3)), P_ATM, p_field=field)
+    for i in range(3):
+        blk = got[:, 90 * i:90 * (i + 1)]
+        assert np.array_equal(blk, per_p[i]) or bk1_errors(blk, per_p[i])[0] <= 1e-13
+
+
+@pytest.mark.parametrize('options', [
+    {'bk1_tmem': True},                                                              # third-body sums in TMEM
+    {'bk1_tmem': True, 'bk1_smem_cap': 0},                                           # every slot in TMEM
+    {'bk1_tmem': True, 'bk1_tmem_block': 128, 'bk1_tmem_ctas': 2, 'bk1_smem_cap': 20},   # two CTAs x 256 columns
+    {'live_cap': 12},                                                                # 86 suspensions / re-activations
+    {'bk1_tmem': True, 'live_cap': 10, 'bk1_smem_cap': 8},
+], ids=['tm', 'tm_all', 'tm_2cta', 'live_cap', 'tm_live_cap'])
+def test_generated_bk1_slot_layouts_on_cpu(options):
+    emu = BK1Emulator('gri30', options)
+    st = synthetic_states(53, 300, seed=7)
+    _check(emu, Oracle('gri30'), st, P_ATM, f'gri30 {options}')
+    sch = emu.stats['bk1_schedule']
+    if options.get('bk1_tmem'):
+        # the emulated tensor memory saw accesses, inside the CTA's column budget and the thread's own lane
+        assert sch['tmem_slots'] > 0 and 0 < emu.tmem_columns_touched() <= 512
+    if options.get('live_cap'):
+        assert sch['peak_live'] <= options['live_cap'] and sch['suspensions'] > 0
+
+
+def test_generated_bk1_largest_mechanism_on_cpu():
+    """EtOHKonnov as shipped: 256-thread CTA, 110 shared + 49 tensor-memory slots, live set capped at 60 (28
+    suspensions), SRI falloff."""
+    emu = BK1Emulator('EtOHKonnov')
+    sch = emu.stats['bk1_schedule']
+    assert emu.block == 256 and sch['tmem_slots'] > 0 and sch['peak_live'] <= 60
+    st = synthetic_states(129, 260, seed=2)
+    _check(emu, Oracle('EtOHKonnov', prefer_ref=False), st, P_ATM, 'EtOHKonnov')
