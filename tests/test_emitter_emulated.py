@@ -25,11 +25,16 @@ def _check(emu, orc, st, p, label):
     return new
 
 
-@pytest.mark.parametrize('mech,prefer_ref', [('LiDryer', True), ('gri30', True), ('H2_Konnov', False)])
+@pytest.mark.parametrize('mech,prefer_ref', [('LiDryer', True), ('gri30', True), ('NH3Konnov_edit', True),
+                                             ('H2_Konnov', False), ('H2_new_mech', False), ('gri30-20', False),
+                                             ('gri30-27', False), ('gri30-35', False), ('heptaneLu88', False)])
 def test_generated_bk1_on_cpu(mech, prefer_ref):
+    """every shipped mechanism (EtOHKonnov and chempolimi_edit have their own tests below), at 1 atm and at 30 bar"""
     emu = BK1Emulator(mech)
+    orc = Oracle(mech, prefer_ref=prefer_ref)
     st = synthetic_states(emu.mech.n_species, 300, seed=11)       # ragged: tail threads re-run the last state
-    _check(emu, Oracle(mech, prefer_ref=prefer_ref), st, P_ATM, mech)
+    _check(emu, orc, st, P_ATM, mech)
+    _check(emu, orc, st[:, :64], 3.0e6, mech + ' 30 bar')
 
 
 def test_generated_bk1_plog_and_pressure_field_on_cpu():
