@@ -95,10 +95,10 @@ def _math_header():
     return text
 
 
-def bk1_source(mech_name, options=None):
+def bk1_source(mech_name, options=None, single_precision=False):
     """BK1 part of the module text (constants, NASA table, kernel) + launch shape, as emit_module plans it"""
     mech = load_mechanism(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech_name + '.yaml'))
-    src, stats = emit_module(mech, None, dict(options or {}))
+    src, stats = emit_module(mech, None, dict(options or {}), single_precision=single_precision)
     bk1 = src[:src.index('kx_rcpM[')]
     bk1 = bk1[:bk1.rindex('\n')]                    # drop the started table line
     m = re.search(r'__launch_bounds__\((\d+), (\d+)\)', bk1)
@@ -106,18 +106,30 @@ def bk1_source(mech_name, options=None):
 
 
 class BK1Emulator:
-    def __init__(self, mech_name, options=None):
-        self.mech, src, self.block, self.stats = bk1_source(mech_name, options)
+    def __init__(self, mech_name, options=None, single_precision=False):
+        """single_precision: the FP32-math kernel of the --single-precision module, run on FP64 buffers ("fpmix");
+        ex2 / lg2 / rcp.approx become exp2f / log2f / 1/x, i.e. the hardware approximations' 2^-22 errors are NOT
+        modelled -- this checks the emitter's log2-space algebra and its immediates, not the MUFU accuracy."""
+        self.sp = bool(single_precision)
+        self.mech, src, self.block, self.stats = bk1_source(mech_name, options, self.sp)
         slots = self.stats['bk1_schedule']['smem_slots']
         src = src.replace('#include <cuda_runtime.h>', '#include "cuda_emu.h"').replace('#include <math_constants.h>', '')
         src = src.replace('#include "kx_math.cuh"', '#include "kx_math_emu.h"').replace('#include "kx_tm.cuh"', '#include "kx_tm_emu.h"')
         if 'kx_tm_emu.h' not in src:
             src = src.replace('#include "kx_math_emu.h"', '#include "kx_math_emu.h"\n#include "kx_tm_emu.h"')
-        assert src.count('extern __shared__ double kx_sm[];') == 1
+        assert src.count('extern __shared__ double kx_sm[];') == (0 if self.sp else 1)
         src = src.replace('extern __shared__ double kx_sm[];', 'double* const kx_sm = emu_smem;')
         src = src.replace('__shared__ unsigned kx_tm_slot;', 'static unsigned kx_tm_slot;')
         src = src.replace('#include "kx_math_emu.h"', f'static double emu_smem[{max(slots, 1)} * {self.block}];\n#include "kx_math_emu.h"', 1)
         has_pool = 'KxParamPool' in src
+        if self.sp:
+            call = ('if (pfield) kx_bk1_f32<double, true>(n, offsetT, offset, (float)pressure_R, (float)P, (float)log(P), '
+                    'state, rates, Tref, pfield);\n    else kx_bk1_f32<double, false>(n, offsetT, offset, (float)pressure_R, '
+                    '(float)P, (float)log(P), state, rates, Tref, nullptr);')
+        else:
+            pool = ', kx_param_pool' if has_pool else ''
+            call = (f'if (pfield) kx_bk1_f64<true>(n, offsetT, offset, pressure_R, P, log(P), state, rates, Tref, pfield{pool});\n'
+                    f'    else kx_bk1_f64<false>(n, offsetT, offset, pressure_R, P, log(P), state, rates, Tref, nullptr{pool});')
         harness = f'''
 extern "C" unsigned emu_tm_columns() {{ return emu_tm_max_col; }}
 extern "C" int emu_bk1(long long n, long long offsetT, long long offset, double pressure_R, double P,
@@ -137,10 +149,7 @@ extern "C" int emu_bk1(long long n, long long offsetT, long long offset, double 
     for (int s = 0; s < {max(slots, 1)}; s++) emu_smem[s * block + threadIdx.x] = nanv;
     const unsigned lane = (((threadIdx.x >> 5) & 3u) << 5) + (threadIdx.x & 31u);
     for (int c = 0; c < 512; c++) emu_tmem[lane][c] = (c & 1) ? 0x7ff8deadu : 0u;
-    if (pfield)
-      kx_bk1_f64<true>(n, offsetT, offset, pressure_R, P, log(P), state, rates, Tref, pfield{', kx_param_pool' if has_pool else ''});
-    else
-      kx_bk1_f64<false>(n, offsetT, offset, pressure_R, P, log(P), state, rates, Tref, nullptr{', kx_param_pool' if has_pool else ''});
+    {call}
   }}
   return 0;
 }}
@@ -151,7 +160,7 @@ extern "C" int emu_bk1(long long n, long long offsetT, long long offset, double 
                               open(os.path.join(HERE, 'kx_tm_emu.h')).read()).encode()).hexdigest()[:16]
         work = os.path.join(tempfile.gettempdir(), f'kx_emu_{os.getuid()}')
         os.makedirs(work, exist_ok=True)
-        lib = os.path.join(work, f'emu_{mech_name}_{key}.so')
+        lib = os.path.join(work, f'emu_{mech_name}{"_sp" if self.sp else ""}_{key}.so')
         if not os.path.exists(lib):
             d = tempfile.mkdtemp(dir=work)
             with open(os.path.join(d, 'kx_math_emu.h'), 'w') as fh:

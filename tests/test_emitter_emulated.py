@@ -81,3 +81,18 @@ def test_generated_bk1_largest_mechanism_on_cpu():
     assert emu.block == 256 and sch['tmem_slots'] > 0 and sch['peak_live'] <= 60
     st = synthetic_states(129, 260, seed=2)
     _check(emu, Oracle('EtOHKonnov', prefer_ref=False), st, P_ATM, 'EtOHKonnov')
+
+
+@pytest.mark.parametrize('mech', ['LiDryer', 'gri30'])
+def test_generated_fp32_math_bk1_on_cpu(mech):
+    """the --single-precision kernel (log2-space FP32 math, constants as immediates) on FP64 buffers, against the
+    FP64 oracle at the stated single-precision bounds (rates 1e-4, heat release 5e-3) over the full
+    T in [300, 2500] K range -- the reference's own FP32 code is NaN / Inf below ~615 K."""
+    emu = BK1Emulator(mech, single_precision=True)
+    st = synthetic_states(emu.mech.n_species, 2000, seed=31)
+    new = emu.production_rates(st, P_ATM)
+    ref = Oracle(mech).production_rates(st, P_ATM)
+    assert np.isfinite(new).all()
+    rate_err, hrr_err = bk1_errors(new, ref)
+    print(f'{mech} FP32-math kernel (emulated) vs FP64 oracle: rates {rate_err:.2e} hrr {hrr_err:.2e}')
+    assert rate_err <= 1e-4 and hrr_err <= 5e-3
