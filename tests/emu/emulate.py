@@ -167,7 +167,7 @@ extern "C" int emu_bk1(long long n, long long offsetT, long long offset, double 
                 fh.write(math)
             with open(os.path.join(d, 'bk1_emu.cpp'), 'w') as fh:
                 fh.write(full)
-            cmd = ['g++', '-std=c++17', '-O1', '-mfma', '-ffp-contract=off', '-shared', '-fPIC', '-w', '-I', d, '-I', HERE,
+            cmd = ['g++', '-std=c++17', '-O0', '-ffp-contract=off', '-shared', '-fPIC', '-w', '-I', d, '-I', HERE,
                    '-o', lib + '.tmp', os.path.join(d, 'bk1_emu.cpp')]
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             if r.returncode != 0:
