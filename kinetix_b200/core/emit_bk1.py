@@ -305,8 +305,13 @@ class BK1Emitter:
     # ---- main --------------------------------------------------------------------------------
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
              reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False,
-             tmem_slots=0, smem_cap=0, tmem_cols=512):
+             tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0):
         """block / min_blocks: launch bounds.
+        cold_uses / cold_slot_cap (experimental, off by default): species that occur in at most `cold_uses` reactions
+          keep their concentration C_k and rate accumulator wdot_k in two SHARED-MEMORY slots instead of registers
+          while they are live, as long as the thread's slots in use stay below `cold_slot_cap`: explicit placement of
+          the values ptxas would otherwise spill to local memory (heptaneLu88: 88 species, 29 slots, 2.7 KB of spill
+          loads at 168 registers while two thirds of its shared-memory budget are idle).
         tmem_slots: > 0: that many doubles per thread of TENSOR MEMORY hold scratch slots beside at most `smem_cap`
           shared-memory slots (large mechanisms: EtOHKonnov needs 210 slots = 1.7 KB per thread, which limits a
           shared-memory-only kernel to 4 warps per SM).  Third-body sums go to tensor memory first, exp(+-g_k) to
@@ -409,9 +414,9 @@ class BK1Emitter:
         free_slots, n_slots = [], (ring if ring else 0)
         free_tm, n_tm = [], 0
 
-        def take_slot(prefer_tm=False):
+        def take_slot(prefer_tm=False, smem_only=False):
             nonlocal n_slots, n_tm
-            for pool in (('t', 's') if prefer_tm else ('s', 't')):
+            for pool in (('s',) if smem_only else ('t', 's') if prefer_tm else ('s', 't')):
                 if pool == 's':
                     if free_slots:
                         return free_slots.pop(0)
@@ -424,6 +429,8 @@ class BK1Emitter:
                     if n_tm < tmem_slots:
                         n_tm += 1
                         return self.TM_BASE + n_tm - 1
+            if smem_only:
+                return None
             raise RuntimeError(f'BK1 emitter: out of scratch slots ({smem_cap} shared + {tmem_slots} tensor memory)')
 
         def release_slot(slot):
@@ -530,6 +537,8 @@ class BK1Emitter:
 
         def collider_val(rx):
             name = collider(rx)
+            if name.startswith('cs'):
+                return CS(int(name[2:]))
             return self.val(eff_slot[name]) if name in eff_slot else name
 
         def ln_collider_val(rx):
@@ -541,6 +550,31 @@ class BK1Emitter:
 
         # ---- per-species live state --------------------------------------------------------------
         used = sorted(first)                                  # species that occur in some reaction
+        # cold species: C_k / wdot_k in shared-memory slots while live (see cold_uses above)
+        mem_cs, mem_wd = {}, {}
+        self.cold_activations = 0
+
+        def CS(k):
+            return f'gs[{mem_cs[k]} * {block}]' if k in mem_cs else f'cs{k}'
+
+        def WD(k):
+            return f'gs[{mem_wd[k]} * {block}]' if k in mem_wd else f'wd{k}'
+
+        def place(k):
+            """decide where species k lives for this live segment"""
+            if not (cold_uses and gibbs_in_smem) or len(uses[k]) > cold_uses:
+                return
+            cap = smem_cap if tmem_slots else cold_slot_cap
+            if (n_slots - len(free_slots)) + 2 + 6 > cap:         # 6: head-room for exp(+-g) of the next activations
+                return
+            a, b = take_slot(smem_only=True), take_slot(smem_only=True)
+            if a is None or b is None:
+                for t in (a, b):
+                    if t is not None:
+                        release_slot(t)
+                return
+            mem_cs[k], mem_wd[k] = a, b
+            self.cold_activations += 1
         w('double ' + ', '.join(f'cs{k}' for k in used) + ';')
         w('double ' + ', '.join(f'wd{k}' for k in used) + ';')
         if not ring:
@@ -566,8 +600,9 @@ class BK1Emitter:
 
         def activate(k, reactivation=False):
             """species k becomes live: concentration, zeroed accumulator, exp(+-g_k/RT)"""
+            place(k)
             if k in self.kept and not reactivation:
-                w(f'cs{k} = w{k} * rho; wd{k} = 0.0;')
+                w(f'{CS(k)} = w{k} * rho; {WD(k)} = 0.0;')
             elif ring and not reactivation:
                 r = rank[k]
                 pending = max(0, min(ring - 1, len(act_order) - 1 - r))
@@ -579,15 +614,15 @@ class BK1Emitter:
             if k in self.kept and not reactivation:
                 pass
             elif reactivation:
-                w(f'cs{k} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); wd{k} = 0.0;')
+                w(f'{CS(k)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
             elif not ring and pin_loads:
                 # volatile max: keeps this activation ordered after the loads issued `prefetch` activations
                 # ahead (volatile asms are not reordered among themselves), so the compiler cannot sink those
                 # loads down to their first use
                 w(f'{{ double t; asm volatile("max.f64 %0, %1, 0d0000000000000000;" : "=d"(t) : "d"(y{k})); '
-                  f'cs{k} = t * ({K(1. / m.species[k].M)} * rho); wd{k} = 0.0; }}')
+                  f'{CS(k)} = t * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0; }}')
             else:
-                w(f'cs{k} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); wd{k} = 0.0;')
+                w(f'{CS(k)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
             if not (need_pos[k] or need_neg[k]):
                 return
             c, _, _ = self.nasa_select(k, gcoef)
@@ -626,19 +661,22 @@ class BK1Emitter:
             add its heat release, free its slots (productionRates.okl:48-62)"""
             c, _, _ = self.nasa_select(k, hcoef)
             if first_flush:
-                w(f'if (live) kx_st_row<{k}>(out, offset, {K(m.species[k].M)} * wd{k});')
+                w(f'if (live) kx_st_row<{k}>(out, offset, {K(m.species[k].M)} * {WD(k)});')
             else:
-                w(f'if (live) kx_add_row<{k}>(out, offset, {K(m.species[k].M)} * wd{k});')
-            w(f'hsum = fma(wd{k}, fma(fma(fma(fma({c[4]}, T, {c[3]}), T, {c[2]}), T, {c[1]}), T, '
+                w(f'if (live) kx_add_row<{k}>(out, offset, {K(m.species[k].M)} * {WD(k)});')
+            w(f'hsum = fma({WD(k)}, fma(fma(fma(fma({c[4]}, T, {c[3]}), T, {c[2]}), T, {c[1]}), T, '
               f'fma({c[5]}, rcpT, {c[0]})), hsum);')
             for slots in (self.eg_slot, self.rg_slot):
                 if gibbs_in_smem and k in slots:
                     release_slot(slots[k])
+            for slots in (mem_cs, mem_wd):
+                if k in slots:
+                    release_slot(slots.pop(k))
 
         def conc_product(nu):
             terms = []
             for k, c in enumerate(nu):
-                terms += [f'cs{k}'] * c
+                terms += [CS(k)] * c
             return ' * '.join(terms)
 
         # species that never occur in a reaction: rate row is zero (the reference's wdot[k] stays 0)
@@ -771,11 +809,11 @@ class BK1Emitter:
                     w(f'    const double q = kf * fma(-kr, {Rr}, {Rf});')
                 for k, v in enumerate(net):
                     if v == 1:
-                        w(f'    wd{k} += q;')
+                        w(f'    {WD(k)} += q;')
                     elif v == -1:
-                        w(f'    wd{k} -= q;')
+                        w(f'    {WD(k)} -= q;')
                     elif v != 0:
-                        w(f'    wd{k} = fma({float(v)}, q, wd{k});')
+                        w(f'    {WD(k)} = fma({float(v)}, q, {WD(k)});')
                 w('  }')
             w('}')
             for k in sorted(by_last.get(pos, [])):
@@ -787,6 +825,8 @@ class BK1Emitter:
 
         self.smem_doubles_per_thread = n_slots if (gibbs_in_smem or ring) else 0
         self.schedule_stats.update(peak_live=peak_live, smem_slots=n_slots, tmem_slots=n_tm)
+        if cold_uses:
+            self.schedule_stats['cold_activations'] = self.cold_activations
         body[flag_pos:flag_pos] = ['  ' + v for v in self._flags.values()]
 
         head = [
