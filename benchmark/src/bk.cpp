@@ -300,14 +300,18 @@ int main(int argc, char** argv)
   int rank = 0;
   std::vector<int> pipes;
   std::vector<pid_t> children;
+  const int n_total = n_states;
   if (gpus > 1) {
-    n_states /= gpus;
+    // the reference gives every rank n_states / size states and drops the remainder (bk.cpp:443); here the first
+    // n_states % gpus workers take one more, so the aggregate really is --n-states
+    n_states = n_total / gpus + (0 < n_total % gpus ? 1 : 0);
     for (int r = 1; r < gpus; r++) {
       int fd[2];
       if (pipe(fd)) return EXIT_FAILURE;
       pid_t pid = fork();
       if (pid == 0) {
         rank = r;
+        n_states = n_total / gpus + (r < n_total % gpus ? 1 : 0);
         close(fd[0]);
         pipes = {fd[1]};
         break;
@@ -425,7 +429,7 @@ int main(int argc, char** argv)
   const double FP64_PEAK = 1.709e13;   // measured DFMA lane-instr/s per B200 (profiles/peaks_r01.json)
   if (!cimode) {
     if (mode == 0 || mode == 1) {
-      const double sps = gpus * (double)n_states * nRep / t_bk1;
+      const double sps = (double)n_total * nRep / t_bk1;
       printf("BK1 (reaction rates) results:\n");
       printf("avg elapsed time: %.5f s\n", t_bk1);
       printf("avg aggregated throughput: %.2f GRXN/s\n", sps * n_reactions / 1e9);
@@ -434,7 +438,7 @@ int main(int argc, char** argv)
         printf("fraction of FP64 roofline (W = 1.4e4 FP64 instr/state): %.3f\n", sps / gpus * 1.4e4 / FP64_PEAK);
     }
     if (mode == 0 || mode == 2) {
-      const double sps = gpus * (double)n_states * nRep / t_bk2;
+      const double sps = (double)n_total * nRep / t_bk2;
       printf("BK2 (transport) results:\n");
       printf("avg elapsed time: %.5f s\n", t_bk2);
       printf("avg aggregated throughput: %.2f GDOF/s\n", sps * (n_species + 2) / 1e9);

@@ -32,12 +32,26 @@ def main(argv=None):
     p.add_argument('--fit-rcpdiffcoeffs', action='store_true')
     p.add_argument('--compile', action='store_true', help='Compile the module with nvcc (libkx_mech.so).')
     p.add_argument('--block-size', type=int, default=0)
+    p.add_argument('--emit-routines', action='store_true',
+                   help='Write the reference-signature device routines (mech.h, rates, enthalpy_RT, heat_capacity_R, '
+                        'conductivity, viscosity, diffusivity) into <output>/routines instead of / beside the kernels.')
+    p.add_argument('--routine-ext', default='cuh', choices=['cuh', 'cpp'],
+                   help="File extension of the routine files; 'cpp' gives the reference's literal names.")
     p.add_argument('--force', action='store_true')
     p.add_argument('--verbose', action='store_true')
     a = p.parse_args(argv)
     if a.target not in ('sm_100a', 'CUDA'):
         sys.exit(f"Error: unsupported --target '{a.target}': kinetix_b200 only emits sm_100a CUDA")
     transport = str(a.transport).lower() not in ('0', 'false', 'no')
+    if a.emit_routines:
+        if a.single_precision:
+            sys.exit('Error: --emit-routines is FP64 only (the FP32-math kernels have no per-routine form)')
+        import os
+        jit.ensure_routines(a.mechanism, os.path.join(a.output, 'routines'), fit_rcp_diff=a.fit_rcpdiffcoeffs,
+                            transport=transport, ext=a.routine_ext, force=a.force, compile_kernels=a.compile,
+                            block_size=a.block_size or 128, verbose=a.verbose)
+        if a.header_only or not a.compile:
+            return 0
     jit.ensure_module(a.mechanism, a.output, fit_rcp_diff=a.fit_rcpdiffcoeffs,
                       single_precision=a.single_precision, block_size=a.block_size,
                       transport=transport and not a.header_only, force=a.force, verbose=a.verbose,

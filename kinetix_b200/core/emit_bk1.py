@@ -305,8 +305,12 @@ class BK1Emitter:
     # ---- main --------------------------------------------------------------------------------
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
              reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False,
-             tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0):
+             tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0, routine=False):
         """block / min_blocks: launch bounds.
+        routine: emit the reference-signature DEVICE FUNCTION `kinetix_species_rates(lnT, T, T2, T3, T4, rcpT, P, lnP,
+          Ci, wdot)` (reference reaction_rates.py:560-562) instead of the kernel: concentrations come from `Ci[]`,
+          rates are ADDED to `wdot[]` (the caller pre-zeroes it, productionRates.okl:40), no state rows, no scratch
+          slots, no heat release.  Same minimal-form arithmetic and liveness schedule (see emit_routines.py).
         cold_uses / cold_slot_cap (experimental, off by default): species that occur in at most `cold_uses` reactions
           keep their concentration C_k and rate accumulator wdot_k in two SHARED-MEMORY slots instead of registers
           while they are live, as long as the thread's slots in use stay below `cold_slot_cap`: explicit placement of
@@ -444,9 +448,10 @@ class BK1Emitter:
             w('__shared__ unsigned kx_tm_slot;')
             w(f'const unsigned tm_alloc = kx_tm_alloc_all<{tmem_cols}>(&kx_tm_slot);')
             w(f'const unsigned tmb = tm_alloc + (((threadIdx.x >> 5) & 3u) << 21) + (threadIdx.x >> 7) * {2 * tmem_slots}u;')
-        w('#ifdef KX_EXP_TABLE')
-        w('kx_exptab_init();')
-        w('#endif')
+        if not routine:
+            w('#ifdef KX_EXP_TABLE')
+            w('kx_exptab_init();')
+            w('#endif')
         if nasa_indexed == 'smem':
             w('__shared__ double kx_nasa_s[KX_NASA_LEN];')
             w('for (int i = threadIdx.x; i < KX_NASA_LEN; i += blockDim.x) kx_nasa_s[i] = kx_nasa_tab[i];')
@@ -458,9 +463,15 @@ class BK1Emitter:
         for name in eff_names.values():
             if eff_smem:
                 eff_slot[name] = take_slot(prefer_tm=True)
-        w('const double T = Tref * kx_ld_stream(state + id);')
-        w('const double rcpT = kx_rcp(T);')
-        w('const double lnT = kx_log(T);')
+        self.routine = routine
+        if routine:
+            assert not (gibbs_in_smem or ring or tmem_slots or live_cap or keep_until)
+            w('const double Pv = P, lnPv = lnP;')
+            w('(void)T2; (void)T3; (void)T4; (void)Pv; (void)lnPv;')
+        else:
+            w('const double T = Tref * kx_ld_stream(state + id);')
+            w('const double rcpT = kx_rcp(T);')
+            w('const double lnT = kx_log(T);')
         w('double rho, Cm;')
         if not eff_smem:
             for name in eff_names.values():
@@ -496,13 +507,20 @@ class BK1Emitter:
         for name in eff_names.values():
             w(f'  double a{name} = 0.0;')
         for k in range(N):
-            w(f'  {"" if k in kept else "const double "}w{k} = fmax(0.0, kx_ld_row<{k}>(sp, offset)) * '
-              f'{K(1. / m.species[k].M)}; rcpMbar += w{k};')
+            if routine:      # w_k = C_k, rho = 1: Cm = sum_k C_k over ALL species (reaction_rates.py:579)
+                w(f'  const double w{k} = Ci[{k}]; rcpMbar += w{k};')
+            else:
+                w(f'  {"" if k in kept else "const double "}w{k} = fmax(0.0, kx_ld_row<{k}>(sp, offset)) * '
+                  f'{K(1. / m.species[k].M)}; rcpMbar += w{k};')
             for vec, name in eff_names.items():
                 if vec[k] != 1:
                     w(f'  a{name} = fma({K(vec[k] - 1)}, w{k}, a{name});')
-        w('  rho = pR * rcpT * kx_rcp(rcpMbar);')
-        w('  Cm = rho * rcpMbar;')
+        if routine:
+            w('  rho = 1.0;')
+            w('  Cm = rcpMbar;')
+        else:
+            w('  rho = pR * rcpT * kx_rcp(rcpMbar);')
+            w('  Cm = rho * rcpMbar;')
         ln_slot, ln_collider = {}, {}
         for name in eff_names.values():
             if eff_smem:
@@ -577,9 +595,10 @@ class BK1Emitter:
             self.cold_activations += 1
         w('double ' + ', '.join(f'cs{k}' for k in used) + ';')
         w('double ' + ', '.join(f'wd{k}' for k in used) + ';')
-        if not ring:
+        if not ring and not routine:
             w('double ' + ', '.join(f'y{k}' for k in used) + ';')
-        w('double hsum = 0.0;')
+        if not routine:
+            w('double hsum = 0.0;')
         act_order = sorted(used, key=lambda k: (first[k], k))      # activation order
         rank = {k: i for i, k in enumerate(act_order)}
         if ring:
@@ -601,7 +620,9 @@ class BK1Emitter:
         def activate(k, reactivation=False):
             """species k becomes live: concentration, zeroed accumulator, exp(+-g_k/RT)"""
             place(k)
-            if k in self.kept and not reactivation:
+            if routine:
+                w(f'{CS(k)} = Ci[{k}]; {WD(k)} = 0.0;')
+            elif k in self.kept and not reactivation:
                 w(f'{CS(k)} = w{k} * rho; {WD(k)} = 0.0;')
             elif ring and not reactivation:
                 r = rank[k]
@@ -611,7 +632,7 @@ class BK1Emitter:
                 if r + ring < len(act_order):
                     nk = act_order[r + ring]
                     w(f'kx_cp_async8(ring_base + {r % ring} * {block} * 8, sp + {nk} * offset);')
-            if k in self.kept and not reactivation:
+            if routine or (k in self.kept and not reactivation):
                 pass
             elif reactivation:
                 w(f'{CS(k)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
@@ -659,6 +680,9 @@ class BK1Emitter:
         def retire(k, first_flush=True):
             """species k leaves the live set (for good, or suspended under live_cap): write / add its rate row,
             add its heat release, free its slots (productionRates.okl:48-62)"""
+            if routine:
+                w(f'wdot[{k}] += {WD(k)};')
+                return
             c, _, _ = self.nasa_select(k, hcoef)
             if first_flush:
                 w(f'if (live) kx_st_row<{k}>(out, offset, {K(m.species[k].M)} * {WD(k)});')
@@ -681,7 +705,7 @@ class BK1Emitter:
 
         # species that never occur in a reaction: rate row is zero (the reference's wdot[k] stays 0)
         for k in range(N):
-            if k not in first:
+            if k not in first and not routine:
                 w(f'if (live) kx_st_row<{k}>(out, offset, 0.0);')
 
         # ---- units in schedule order ---------------------------------------------------------------
@@ -696,7 +720,7 @@ class BK1Emitter:
         loaded = set()
 
         def issue_loads(upto_rank):
-            if ring:
+            if ring or routine:
                 return
             for k in act_order[:upto_rank + 1]:
                 if k not in loaded and k not in self.kept:
@@ -819,7 +843,8 @@ class BK1Emitter:
             for k in sorted(by_last.get(pos, [])):
                 retire(k, first_flush=seg_index[(k, 'end', pos)] == 0)
                 live_now -= 1
-        w(f'if (live) kx_st_stream(rates + id, {K(-const.R_GAS)} * T * hsum);')
+        if not routine:
+            w(f'if (live) kx_st_stream(rates + id, {K(-const.R_GAS)} * T * hsum);')
         if tmem_slots:
             w(f'kx_tm_free_all<{tmem_cols}>(tm_alloc);')
 
@@ -829,6 +854,17 @@ class BK1Emitter:
             self.schedule_stats['cold_activations'] = self.cold_activations
         body[flag_pos:flag_pos] = ['  ' + v for v in self._flags.values()]
 
+        if routine:
+            head = [
+                f'// kinetix_species_rates: {m.name}, {N} species / {m.n_reactions} reactions; {self.stats["exp"]} kx_exp, '
+                f'{self.stats["exp_wide"]} wide exp, {self.stats["log"]} log, {self.stats["rcp"]} rcp per call; '
+                f'peak live species {peak_live}',
+                '__KINETIX_DEVICE__ __KINETIX_INLINE__ void kinetix_species_rates(const cfloat lnT, const cfloat T, '
+                'const cfloat T2, const cfloat T3, const cfloat T4, const cfloat rcpT, const cfloat P, const cfloat lnP, '
+                'const cfloat* Ci, cfloat* wdot)',
+                '{',
+            ]
+            return '\n'.join(head + body + ['}', ''])
         head = [
             f'// BK1 (species production rates): {m.name}, {N} species / {m.n_reactions} reactions; '
             f'{self.stats["exp"]} kx_exp, {self.stats["exp_wide"]} wide exp, {self.stats["log"]} log, '

@@ -55,7 +55,7 @@ def _emitter_sources():
     core = os.path.join(PKG, 'core')
     out = [os.path.join(core, f) for f in os.listdir(core) if f.endswith('.py')]
     out += [os.path.join(core, 'data', f) for f in os.listdir(os.path.join(core, 'data'))]
-    out += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')]
+    out += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh') or f.endswith('.cu')]
     return out
 
 
@@ -122,6 +122,46 @@ def ensure_module(mechanism_path, output_dir=None, fit_rcp_diff=False, single_pr
                                      '-cudart', 'shared', '-I', CSRC, '-Xptxas', '-v', '-o', lib, cu,
                                      '-Xlinker', f'-rpath={os.path.join(CUDA_HOME, "lib64")}'] + list(extra_nvcc)
         log = _run(cmd, f'nvcc ({mech.name})')
+        with open(os.path.join(out, 'ptxas.log'), 'w') as fh:
+            fh.write(log)
+        if verbose:
+            sys.stderr.write(log)
+    with open(stamp, 'w') as fh:
+        fh.write(digest)
+    return out
+
+
+def ensure_routines(mechanism_path, output_dir=None, fit_rcp_diff=False, transport=True, ext='cuh', force=False,
+                    compile_kernels=False, block_size=128, verbose=False):
+    """Write the reference-signature device routines of one mechanism (core/emit_routines.py: mech.h, rates,
+    enthalpy_RT, heat_capacity_R, conductivity, viscosity, diffusivity + umbrella header) into `output_dir`
+    (default: <cache>/<tag>/routines); with compile_kernels also build libkx_routines.so = the reference's three
+    OKL kernels restated in CUDA around those routines (csrc/kx_routine_kernels.cu).  Returns the directory."""
+    from .core.emit_routines import write_routines
+    from .core.mechanism import load_mechanism
+    from .core.transport_fit import fit_transport
+
+    mechanism_path = os.path.abspath(mechanism_path)
+    out = output_dir or os.path.join(default_cache(), module_tag(mechanism_path, fit_rcp_diff), 'routines')
+    lib = os.path.join(out, 'libkx_routines.so')
+    opts = dict(fit_rcp_diff=bool(fit_rcp_diff), transport=bool(transport), ext=ext, block_size=int(block_size),
+                kind='routines')
+    digest = _hash_files(_emitter_sources() + [mechanism_path], json.dumps(opts, sort_keys=True))
+    stamp = os.path.join(out, '.hash')
+    fresh = os.path.exists(stamp) and open(stamp).read() == digest
+    if fresh and not force and (os.path.exists(lib) or not compile_kernels):
+        return out
+    mech = load_mechanism(mechanism_path)
+    fits = fit_transport(mech, reciprocal_diffusivity=fit_rcp_diff) if transport else None
+    _, stats = write_routines(mech, fits, out, ext=ext)
+    if compile_kernels:
+        if not transport:
+            raise RuntimeError('ensure_routines: the wrapper kernels need the transport routines')
+        cmd = [NVCC] + ARCH_FLAGS + ['-O3', '-lineinfo', '-std=c++17', '-shared', '-Xcompiler', '-fPIC', '-cudart', 'shared',
+                                     '-I', out, f'-Dp_BLOCKSIZE={int(block_size)}', '-Xptxas', '-v', '-o', lib,
+                                     os.path.join(CSRC, 'kx_routine_kernels.cu'),
+                                     '-Xlinker', f'-rpath={os.path.join(CUDA_HOME, "lib64")}']
+        log = _run(cmd, f'nvcc routines ({mech.name})')
         with open(os.path.join(out, 'ptxas.log'), 'w') as fh:
             fh.write(log)
         if verbose:
