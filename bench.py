@@ -12,6 +12,11 @@ value = (states per GPU x N GPUs) / (device time of one step, max over ranks)  [
 the per-kernel rates are reported beside it.  States are independent: the batch is sharded over the
 GPUs, there is no collective on the data path ("scaling": "weak").
 
+Beside the headline the same line carries `configs`: BASELINE.json's other configurations measured in the same
+process (LiDryer BK1 8 Mi states/GPU in FP64 and with FP32 math -- the bandwidth-leaning regime --, EtOHKonnov
+BK1+BK2 16 Mi states/GPU, GRI-3.0 BK1 with FP32 math, and a STRONG-scaling point: 16 Mi GRI states in total cut
+into per-rank shards by kinetix_b200/sharding.py), each with the roofline fraction of the pipe that bounds it.
+
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -32,14 +37,12 @@ METRIC = 'BK1+BK2 states/sec (GRI-3.0, FP64)'
 UNIT = 'states/s'
 P_ATM = 101325.0
 
-# Algorithmic FP64-pipe work per state (lane instructions: DFMA/DMUL/DADD), minimal form with the
-# reference's libdevice-class costs -- SURVEY.md 8(d), derivation in DESIGN.md "Roofline".
-W_FP64 = {'gri30': {'bk1': 1.4e4, 'bk2': 2.47e4}}
-# FP64-pipe lane instructions our kernels actually EXECUTE per state (ncu smsp__inst_executed_pipe_fp64 x 32 / states,
-# profiles/ncu_r01_bk1_v6.txt, ncu_r01_bk2_v4.txt): fewer than W (shared exps in BK1; rank-12 Wilke factorisation and
-# the 2-instruction pair reciprocal in BK2), so `frac` (by W) exceeds the hardware-side pipe utilisation,
-# which is reported next to it as `frac_executed`.
-EXEC_FP64 = {'gri30': {'bk1': 1.13e4, 'bk2': 1.82e4}}
+# FP64-pipe lane instructions per state (DFMA/DMUL/DADD/DSETP, one per lane) the REFERENCE's arithmetic costs as its
+# generator emits it, with libdevice-class transcendental costs (probed SASS of the reference-style
+# kernel).  Kept for continuity with round 1 (`frac_reference_W`); the roofline's `frac` uses the count of the
+# MINIMAL form known today = what our kernels execute (shared exps, low-rank Wilke, 2-instruction pair reciprocal),
+# so that redundant arithmetic can never inflate the fraction ("use the minimal-form W").
+W_REFERENCE = {'gri30': {'bk1': 1.89e4, 'bk2': 2.47e4}}
 
 
 def read_json(path):
@@ -52,11 +55,11 @@ def read_json(path):
 
 def fp64_peak():
     """Measured DFMA issue peak of this pool's B200 [lane-instr/s] (tools/peaks.cu -> profiles/peaks_r01.json);
-    nominal 148 SM x 64 lanes x 1.965 GHz if the measurement is absent."""
+    nominal 148 SM x 64 lanes x 1.965 GHz if the measurement is absent.  MEASURED_PEAKS.json has no FP64 entry."""
     pk = read_json(os.path.join(ROOT, 'profiles', 'peaks_r01.json'))
     if pk and 'dfma_lane_instr_per_s_sustained_3s' in pk:
-        return float(pk['dfma_lane_instr_per_s_sustained_3s']), 'measured (profiles/peaks_r01.json)'
-    return 148 * 64 * 1.965e9, 'nominal'
+        return float(pk['dfma_lane_instr_per_s_sustained_3s']), 'measured DFMA issue rate (tools/peaks.cu -> profiles/peaks_r01.json)'
+    return 148 * 64 * 1.965e9, 'nominal 148 SM x 64 lanes x 1.965 GHz'
 
 
 def hbm_peak():
@@ -64,6 +67,13 @@ def hbm_peak():
     if pk and 'hbm_gbs' in pk:
         return float(pk['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def mufu_peak():
+    pk = read_json(os.path.join(ROOT, 'profiles', 'peaks_r01.json'))
+    if pk and 'mufu_ex2_lane_instr_per_s' in pk:
+        return float(pk['mufu_ex2_lane_instr_per_s'])
+    return 148 * 16 * 1.965e9
 
 
 class ClockSampler:
@@ -271,6 +281,286 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
+class Bench:
+    """per-process state of the CUDA arm: torch, the host mirror, rank / world, collectives for timing only"""
+
+    def __init__(self, args):
+        import torch
+        import kinetix_b200.host as kinetix
+        self.torch, self.kinetix, self.args = torch, kinetix, args
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device; the product has no CPU path (use --impl reference)')
+        torch.cuda.set_device(self.local)
+        self.all_cpus = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+        self.numa = bind_to_gpu_numa_node(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+            self.dist = dist
+        self.launches = 0
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device='cuda')
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def sum_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device='cuda')
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def init_mechanism(self, mech, single_precision=False):
+        """rank 0 generates / compiles a missing module first (kinetix.cpp:290-296), then everybody loads it"""
+        k = self.kinetix
+        path = os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech + '.yaml')
+        if self.rank == 0:
+            k.prepare(path, single_precision=single_precision)
+        self.barrier()
+        k.init(path, device_id=self.local, single_precision=single_precision)
+        N = k.nSpecies()
+        k.build(P_ATM, 1.0, [1.0 / N] * N, True)
+        return N
+
+    def synthetic_states(self, N, S, dtype=None, seed_offset=0):
+        torch = self.torch
+        gen = torch.Generator(device='cuda')
+        gen.manual_seed(1234 + self.rank + 1000 * seed_offset)
+        state = torch.empty((N + 1, S), dtype=torch.float64, device='cuda')
+        state[0].uniform_(300.0, 2500.0, generator=gen)
+        state[1:].uniform_(0.0, 1.0, generator=gen)
+        state[1:] /= state[1:].sum(dim=0, keepdim=True)
+        return state if dtype in (None, torch.float64) else state.to(dtype)
+
+    def time_kernels(self, N, S, steps, warmup, state, storage_dtype=0, bk2=True, sampler=None):
+        """`warmup` untimed + `steps` timed passes of BK1 (+ BK2) over `state`; CUDA events on the launching stream,
+        barrier + synchronize on both sides, max over ranks.  Returns (ms per step, ms BK1, ms BK2, buffers)."""
+        torch, k = self.torch, self.kinetix
+        rates = torch.empty_like(state)
+        visc = torch.empty(max(S, 1), dtype=state.dtype, device='cuda')
+        cond = torch.empty_like(visc)
+        rhoD = torch.empty((N, max(S, 1)), dtype=state.dtype, device='cuda') if bk2 else None
+
+        def step(ev=None):
+            if ev:
+                ev[0].record()
+            k.productionRates(S, S, S, 1.0, state, rates, dtype=storage_dtype)
+            if ev:
+                ev[1].record()
+            if bk2:
+                k.mixtureAvgTransportProps(S, S, S, 1.0, state, visc, cond, rhoD, dtype=storage_dtype)
+            if ev:
+                ev[2].record()
+
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.3)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        self.barrier()
+        for i in range(steps):
+            step(evs[i])
+        self.barrier()
+        self.launches += steps * (2 if bk2 else 1)
+        total_ms = evs[0][0].elapsed_time(evs[-1][2])
+        t1 = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+        t2 = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+        total_ms, t1, t2 = self.max_over_ranks([total_ms, t1, t2])
+        assert bool(torch.isfinite(rates[:, :1024].double()).all()), 'BK1 produced non-finite rates'
+        if bk2:
+            assert bool(torch.isfinite(rhoD[:, :1024].double()).all()), 'BK2 produced non-finite coefficients'
+        return total_ms / steps, t1, t2, (rates, visc, cond, rhoD)
+
+
+def module_counts(kinetix):
+    """static SASS census written next to the loaded module by the build (kinetix_b200/sass.py); None if absent or
+    if it does not belong to this module's source"""
+    from kinetix_b200 import sass
+    return sass.read_counts(os.path.dirname(kinetix.modulePath()))
+
+
+def profiled_counts(kinetix):
+    """executed FP64 instructions / DRAM traffic per state measured with ncu (tools/ncu_counts.py ->
+    profiles/counts_r02.json), valid ONLY for the module source they were measured on"""
+    from kinetix_b200 import sass
+    tab = read_json(os.path.join(ROOT, 'profiles', 'counts_r02.json')) or {}
+    try:
+        sha = sass.source_hash(os.path.dirname(kinetix.modulePath()))
+    except Exception:
+        return None, 'module source not found'
+    entry = tab.get(sha)
+    if entry is None:
+        return None, ('stale: profiles/counts_r02.json has no entry for this module source (kernels changed since the '
+                      'last tools/ncu_counts.py run)')
+    return entry, 'profiles/counts_r02.json (ncu, same module source)'
+
+
+def fp64_roofline(kernel, rate, N, W_exec, W_ref, traffic_per_state, S, note):
+    """FP64-pipe roofline of one kernel: achieved = W x states/s (as TFLOP/s, one lane instruction = one DFMA = 2
+    flop) against the measured DFMA issue peak."""
+    peak, peak_src = fp64_peak()
+    hbm, hbm_src = hbm_peak()
+    alg_bytes = {'bk1': 2 * (N + 1) * 8, 'bk2': (2 * N + 3) * 8}[kernel]
+    out = {'bound': 'fp64', 'kernel': 'kx_bk1_f64' if kernel == 'bk1' else 'kx_bk2<double>', 'unit': 'TFLOP/s',
+           'peak': peak * 2 / 1e12, 'peak_source': peak_src, 'states_per_s': rate,
+           'fp64_lane_instr_per_state': W_exec, 'work_source': note,
+           'traffic': traffic_per_state * S if traffic_per_state else None,
+           'algorithmic_bytes_per_launch': alg_bytes * S,
+           'hbm': {'achieved': rate * alg_bytes / 1e9, 'peak': hbm, 'unit': 'GB/s', 'frac': rate * alg_bytes / 1e9 / hbm,
+                   'bytes_per_state': alg_bytes, 'peak_source': hbm_src}}
+    if W_exec:
+        out['achieved'] = rate * W_exec * 2 / 1e12
+        out['frac'] = rate * W_exec / peak
+        out['roofline_states_per_s'] = peak / W_exec
+    else:
+        out['achieved'] = out['frac'] = None
+    if W_ref:
+        out['frac_reference_W'] = rate * W_ref / peak
+        out['reference_fp64_lane_instr_per_state'] = W_ref
+    return out
+
+
+def bandwidth_probe(b, nbytes=256 << 20, reps=4):
+    """host<->device copy rate of this rank's GPU from pinned memory allocated on its NUMA-local cores: each rank
+    ALONE (the others wait) and ALL ranks at once -- what bounds the end-to-end path when several GPUs share a host"""
+    torch = b.torch
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+
+    def rate(direction):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if direction == 'h2d':
+                d.copy_(h, non_blocking=True)
+            else:
+                h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+        return nbytes * reps / (time.perf_counter() - t0) / 1e9
+
+    rate('h2d'); rate('d2h')
+    alone = [0.0, 0.0]
+    for r in range(b.world):
+        b.barrier()
+        if r == b.rank:
+            alone = [rate('h2d'), rate('d2h')]
+    b.barrier()
+    together = [rate('h2d'), rate('d2h')]
+    b.barrier()
+    # bidirectional, all ranks: what the pipelined e2e path actually does
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        with torch.cuda.stream(s1):
+            d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2 = h  # same buffer is fine for a rate probe
+            h2.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    bidir = nbytes * reps / (time.perf_counter() - t0) / 1e9
+    sums = b.sum_over_ranks(alone + together + [bidir])
+    mins = [-x for x in b.max_over_ranks([-v for v in alone + together + [bidir]])]
+    del h, d
+    return {'unit': 'GB/s', 'bytes_per_copy': nbytes,
+            'alone_h2d_mean': sums[0] / b.world, 'alone_d2h_mean': sums[1] / b.world,
+            'alone_h2d_min': mins[0], 'alone_d2h_min': mins[1],
+            'all_ranks_h2d_sum': sums[2], 'all_ranks_d2h_sum': sums[3],
+            'all_ranks_h2d_min': mins[2], 'all_ranks_d2h_min': mins[3],
+            'all_ranks_bidirectional_each_way_sum': sums[4], 'all_ranks_bidirectional_each_way_min': mins[4]}
+
+
+def extra_configs(b, main, steps, warmup):
+    """BASELINE.json configs 3, 4, 5 next to the headline (1, 2): same timing rules, fewer steps."""
+    torch, k, args = b.torch, b.kinetix, b.args
+    peak, _ = fp64_peak()
+    hbm, _ = hbm_peak()
+    out = []
+
+    def entry(name, mech, S, sp, storage, bk2, note):
+        N = b.init_mechanism(mech, single_precision=sp)
+        tdt = torch.float32 if storage == 1 else torch.float64
+        state = b.synthetic_states(N, S, dtype=tdt)
+        ms, t1, t2, bufs = b.time_kernels(N, S, steps, warmup, state, storage_dtype=storage, bk2=bk2)
+        counts = module_counts(k) or {}
+        prof, _ = profiled_counts(k)
+        size = 4 if storage == 1 else 8
+        e = {'name': name, 'mechanism': mech, 'n_species': N, 'n_reactions': k.nReactions(),
+             'precision': ('fp32 math, fp32 buffers' if storage == 1 else 'fp32 math, fp64 buffers (fpmix)') if sp else 'fp64',
+             'states_per_gpu': S, 'n_gpus': b.world, 'steps': steps, 'warmup': warmup, 'note': note,
+             'bk1_ms': t1, 'bk1_states_per_s': S * b.world / (t1 * 1e-3),
+             'module': os.path.relpath(k.modulePath(), ROOT)}
+        bytes1 = 2 * (N + 1) * size
+        r1 = S / (t1 * 1e-3)
+        e['bk1_hbm'] = {'achieved': r1 * bytes1 / 1e9, 'peak': hbm, 'unit': 'GB/s', 'frac': r1 * bytes1 / 1e9 / hbm,
+                        'bytes_per_state': bytes1}
+        c1 = counts.get('bk1') or {}
+        if not sp and c1.get('fp64'):
+            e['bk1_fp64'] = {'fp64_lane_instr_per_state': c1['fp64'], 'frac': r1 * c1['fp64'] / peak,
+                             'work_source': 'static SASS count of the loaded module (straight-line kernel)'}
+        if sp and c1.get('mufu'):
+            e['bk1_mufu'] = {'mufu_lane_instr_per_state': c1['mufu'], 'frac': r1 * c1['mufu'] / mufu_peak(),
+                             'fp32_lane_instr_per_state': c1.get('ffma')}
+        e['bk1_bound'] = max((('hbm', e['bk1_hbm']['frac']), ('fp64', e.get('bk1_fp64', {}).get('frac', 0)),
+                              ('mufu', e.get('bk1_mufu', {}).get('frac', 0))), key=lambda x: x[1])[0]
+        if bk2:
+            r2 = S / (t2 * 1e-3)
+            bytes2 = (2 * N + 3) * size
+            e.update({'bk2_ms': t2, 'bk2_states_per_s': S * b.world / (t2 * 1e-3), 'ms_per_step': ms,
+                      'states_per_s': S * b.world / (ms * 1e-3),
+                      'bk2_hbm': {'achieved': r2 * bytes2 / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                                  'frac': r2 * bytes2 / 1e9 / hbm, 'bytes_per_state': bytes2}})
+            if prof and prof.get('bk2_fp64_per_state'):
+                e['bk2_fp64'] = {'fp64_lane_instr_per_state': prof['bk2_fp64_per_state'],
+                                 'frac': r2 * prof['bk2_fp64_per_state'] / peak,
+                                 'work_source': 'ncu smsp__inst_executed_pipe_fp64 on this module source'}
+        del state, bufs
+        torch.cuda.empty_cache()
+        out.append(e)
+
+    free = torch.cuda.mem_get_info()[0]
+    entry('config 3: small H2/O2 mechanism, BK1, 8 Mi states per GPU (64 Mi on 8), FP64', 'LiDryer', 1 << 23, False, 0, False,
+          'bandwidth-leaning regime starts with FP32 math (next entry)')
+    entry('config 3 (FP32 math, FP64 buffers)', 'LiDryer', 1 << 23, True, 0, False, 'HBM-bound: see bk1_hbm.frac')
+    etoh_S = 1 << 24
+    need = 3 * 130 * etoh_S * 8 * 1.05
+    if free < need:
+        etoh_S = 1 << 22
+    entry('config 4: largest shipped hydrocarbon mechanism, BK1 + BK2, 16 Mi states per GPU, FP64', 'EtOHKonnov', etoh_S,
+          False, 0, True, '' if etoh_S == 1 << 24 else 'reduced to 4 Mi states: not enough free device memory')
+    entry('config 5: GRI-3.0 BK1, FP32 math with FP64 buffers (fpmix), 16 Mi states per GPU', 'gri30', args.n_states, True, 0,
+          False, 'FP64 point of the sweep = the headline bk1_states_per_s')
+    entry('config 5: GRI-3.0 BK1, FP32 math with FP32 buffers, 16 Mi states per GPU', 'gri30', args.n_states, True, 1,
+          False, '')
+    # strong scaling: a FIXED total of 16 Mi GRI-3.0 states cut into contiguous per-rank shards
+    from kinetix_b200.sharding import shard_of
+    total = 1 << 24
+    lo, hi = shard_of(total, b.rank, b.world)
+    N = b.init_mechanism('gri30')
+    state = b.synthetic_states(N, hi - lo, seed_offset=7)
+    ms, t1, t2, bufs = b.time_kernels(N, hi - lo, steps, warmup, state)
+    out.append({'name': 'strong scaling: 16 Mi GRI-3.0 states in total, BK1 + BK2, FP64', 'mechanism': 'gri30',
+                'scaling': 'strong', 'total_states': total, 'n_gpus': b.world, 'states_this_rank': hi - lo,
+                'ms_per_step': ms, 'states_per_s': total / (ms * 1e-3), 'bk1_states_per_s': total / (t1 * 1e-3),
+                'bk2_states_per_s': total / (t2 * 1e-3), 'steps': steps, 'warmup': warmup,
+                'partition': 'kinetix_b200.sharding.shard_of: contiguous ranges, remainder spread over the first ranks'})
+    del state, bufs
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -282,86 +572,29 @@ def main():
     ap.add_argument('--n-states', type=int, default=1 << 24, help='states per GPU')
     ap.add_argument('--e2e-states', type=int, default=1 << 22, help='states per GPU per end-to-end step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--configs', default='all', choices=['all', 'none'],
+                    help="'none' skips the extra BASELINE configurations (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
     if args.impl == 'reference':
         return run_reference_arm(args, real_stdout)
 
-    import torch
-    import kinetix_b200.host as kinetix
+    b = Bench(args)
+    torch, kinetix, rank, world = b.torch, b.kinetix, b.rank, b.world
+    N = b.init_mechanism(args.mechanism)
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device; the product has no CPU path (use --impl reference)')
-    torch.cuda.set_device(local)
-    all_cpus = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
-    numa = bind_to_gpu_numa_node(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    mech_yaml = os.path.join(ROOT, 'kinetix_b200', 'mechanisms', args.mechanism + '.yaml')
-    kinetix.init(mech_yaml, device_id=local)
-    N = kinetix.nSpecies()
-    kinetix.build(P_ATM, 1.0, [1.0 / N] * N, True)
-
-    # ---- synthetic states, resident in HBM (this rank's shard) ----
+    # ---- headline: synthetic states resident in HBM (this rank's shard), BK1 + BK2 ----
     S = args.n_states
-    gen = torch.Generator(device='cuda')
-    gen.manual_seed(1234 + rank)
-    state = torch.empty((N + 1, S), dtype=torch.float64, device='cuda')
-    state[0].uniform_(300.0, 2500.0, generator=gen)
-    state[1:].uniform_(0.0, 1.0, generator=gen)
-    state[1:] /= state[1:].sum(dim=0, keepdim=True)
-    rates = torch.empty_like(state)
-    visc = torch.empty(S, dtype=torch.float64, device='cuda')
-    cond = torch.empty_like(visc)
-    rhoD = torch.empty((N, S), dtype=torch.float64, device='cuda')
-
-    def step(ev=None):
-        if ev:
-            ev[0].record()
-        kinetix.productionRates(S, S, S, 1.0, state, rates)
-        if ev:
-            ev[1].record()
-        kinetix.mixtureAvgTransportProps(S, S, S, 1.0, state, visc, cond, rhoD)
-        if ev:
-            ev[2].record()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    barrier()
-    for i in range(args.steps):
-        step(evs[i])
-    barrier()
+    state = b.synthetic_states(N, S)
+    sampler = ClockSampler(b.local) if rank == 0 else None
+    ms_per_step, t_bk1, t_bk2, (rates, visc, cond, rhoD) = b.time_kernels(N, S, args.steps, args.warmup, state, sampler=sampler)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = evs[0][0].elapsed_time(evs[-1][2])
-    t_bk1 = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    t_bk2 = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
-    tt = torch.tensor([total_ms, t_bk1, t_bk2], dtype=torch.float64, device='cuda')
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms, t_bk1, t_bk2 = tt.tolist()
-    ms_per_step = total_ms / args.steps
     value = S * world / (ms_per_step * 1e-3)
-
-    # sanity: results are finite (catches a kernel that did not run)
-    assert bool(torch.isfinite(rates[:, :1024]).all()) and bool(torch.isfinite(rhoD[:, :1024]).all())
+    headline_launches = b.launches
+    counts = module_counts(kinetix)
+    prof, prof_src = profiled_counts(kinetix)
+    module_path = kinetix.modulePath()
 
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region) ----
     Se = min(args.e2e_states, S)
@@ -371,99 +604,97 @@ def main():
     h_cond = torch.empty(Se, dtype=torch.float64).pin_memory()
     h_rhoD = torch.empty((N, Se), dtype=torch.float64).pin_memory()
 
-    def e2e_step():
+    def e2e_two_calls():
         kinetix.productionRatesHost(Se, Se, Se, 1.0, h_state, h_rates)
         kinetix.mixtureAvgTransportPropsHost(Se, Se, Se, 1.0, h_state, h_visc, h_cond, h_rhoD)
 
-    def e2e_fused_step():
+    def e2e_one_upload():
         kinetix.ratesAndTransportHost(Se, Se, Se, 1.0, h_state, h_rates, h_visc, h_cond, h_rhoD)
 
     e2e_steps = max(3, min(args.steps, 5))
 
     def time_e2e(fn):
         fn()
-        barrier()
+        b.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             fn()
-        barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return Se * world * e2e_steps / float(t.item())
+        b.barrier()
+        t = b.max_over_ranks([time.perf_counter() - t0])[0]
+        return Se * world * e2e_steps / t
 
-    e2e_value = time_e2e(e2e_step)
-    e2e_fused = time_e2e(e2e_fused_step)
-    h2d = 2 * (N + 1) * Se * 8                      # the state slab is uploaded once per kernel
-    d2h = ((N + 1) + (N + 2)) * Se * 8
+    e2e_two = time_e2e(e2e_two_calls)
+    e2e_one = time_e2e(e2e_one_upload)
     assert torch.equal(h_rates[:, :256], rates[:, :256].cpu())
+    probe = bandwidth_probe(b)
+    del h_state, h_rates, h_visc, h_cond, h_rhoD, state, rates, visc, cond, rhoD
+    torch.cuda.empty_cache()
+
+    configs = None
+    if args.configs == 'all':
+        try:
+            configs = extra_configs(b, None, steps=max(3, min(args.steps, 5)), warmup=3)
+        except Exception as e:          # the extra configurations never take the headline down with them
+            configs = [{'error': f'{type(e).__name__}: {e}'}]
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        if b.dist is not None:
+            b.dist.destroy_process_group()
         return 0
 
-    peak, peak_src = fp64_peak()
-    hbm, hbm_src = hbm_peak()
-    W = W_FP64.get(args.mechanism, {'bk1': float('nan'), 'bk2': float('nan')})
     bk1_rate = S / (t_bk1 * 1e-3)
     bk2_rate = S / (t_bk2 * 1e-3)
     dominant = 'bk2' if t_bk2 >= t_bk1 else 'bk1'
-    dom_rate, dom_t = (bk2_rate, t_bk2) if dominant == 'bk2' else (bk1_rate, t_bk1)
-    alg_bytes = {'bk1': 2 * (N + 1) * 8, 'bk2': (2 * N + 3) * 8}
-
-    traffic_tab = read_json(os.path.join(ROOT, 'profiles', 'traffic_r01.json')) or {}
-
-    def traffic(kernel):
-        """DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch's state count"""
-        t = traffic_tab.get({'bk1': 'kx_bk1_f64', 'bk2': 'kx_bk2'}[kernel]) if args.mechanism == 'gri30' else None
-        if not t:
-            return None
-        return (t['dram_read_bytes'] + t['dram_write_bytes']) / t['states'] * S
-
-    def fp64_roofline(kernel, rate):
-        ach = rate * W[kernel] * 2 / 1e12        # FP64 TFLOP/s counting one lane instruction as 2 flop (DFMA)
-        pk = peak * 2 / 1e12
-        return {'bound': 'fp64', 'kernel': 'kx_bk1_f64' if kernel == 'bk1' else 'kx_bk2<double>', 'achieved': ach, 'peak': pk, 'unit': 'TFLOP/s',
-                'frac': ach / pk, 'traffic': traffic(kernel), 'fp64_lane_instr_per_state': W[kernel],
-                'executed_fp64_lane_instr_per_state': EXEC_FP64.get(args.mechanism, {}).get(kernel),
-                'frac_executed': (rate * EXEC_FP64[args.mechanism][kernel] / peak
-                                  if args.mechanism in EXEC_FP64 else None),
-                'states_per_s': rate, 'roofline_states_per_s': peak / W[kernel], 'peak_source': peak_src,
-                'hbm': {'achieved': rate * alg_bytes[kernel] / 1e9, 'peak': hbm, 'unit': 'GB/s',
-                        'frac': rate * alg_bytes[kernel] / 1e9 / hbm, 'bytes_per_state': alg_bytes[kernel],
-                        'peak_source': hbm_src}}
-
+    W_ref = W_REFERENCE.get(args.mechanism, {})
+    W1 = (counts or {}).get('bk1', {}).get('fp64') if counts else None
+    W2 = prof.get('bk2_fp64_per_state') if prof else None
+    tr1 = prof.get('bk1_dram_bytes_per_state') if prof else None
+    tr2 = prof.get('bk2_dram_bytes_per_state') if prof else None
+    roof = {
+        'bk1': fp64_roofline('bk1', bk1_rate, N, W1, W_ref.get('bk1'), tr1, S,
+                             'static SASS count of the loaded module (straight-line kernel: static = executed)'
+                             if W1 else 'unknown: counts.json missing beside the module'),
+        'bk2': fp64_roofline('bk2', bk2_rate, N, W2, W_ref.get('bk2'), tr2, S, prof_src),
+    }
+    other = 'bk1' if dominant == 'bk2' else 'bk2'
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args),
         'bk1_states_per_s': bk1_rate * world, 'bk2_states_per_s': bk2_rate * world,
         'bk1_ms': t_bk1, 'bk2_ms': t_bk2,
-        'bk1_grxn_per_s': bk1_rate * world * kinetix.nReactions() / 1e9,
+        'bk1_grxn_per_s': bk1_rate * world * 325 / 1e9 if args.mechanism == 'gri30' else None,
         'bk2_gdof_per_s': bk2_rate * world * (N + 2) / 1e9,
-        'roofline': fp64_roofline(dominant, dom_rate),
-        'roofline_other': fp64_roofline('bk1' if dominant == 'bk2' else 'bk2',
-                                        bk1_rate if dominant == 'bk2' else bk2_rate),
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'states_per_step': Se * world, 'api': 'kx_production_rates_host + kx_mixture_avg_transport_props_host',
-                'fused_value': e2e_fused, 'fused_api': 'kx_rates_and_transport_host (one state upload)',
-                'fused_h2d_bytes_per_step': (N + 1) * Se * 8},
-        'gpu_launches': 2 * args.steps,
+        'roofline': roof[dominant],
+        'roofline_other': roof[other],
+        'e2e': {'value': e2e_one, 'unit': UNIT,
+                'h2d_bytes_per_step': (N + 1) * Se * 8 * world, 'd2h_bytes_per_step': ((N + 1) + (N + 2)) * Se * 8 * world,
+                'states_per_step': Se * world,
+                'api': 'kx_rates_and_transport_host: BK1 + BK2 of the same host-resident states, ONE upload of the state '
+                       'slab, 128 Ki-state chunks pipelined H2D | kernels | D2H on 4 streams',
+                'two_call_value': e2e_two,
+                'two_call_api': 'kx_production_rates_host + kx_mixture_avg_transport_props_host (the reference\'s two calls: '
+                                'the state slab is uploaded twice)',
+                'two_call_h2d_bytes_per_step': 2 * (N + 1) * Se * 8 * world,
+                'bytes_are': 'whole job (all ranks)',
+                'host_link_probe': probe},
+        'gpu_launches': headline_launches,
+        'gpu_launches_all_configs': b.launches,
         'clocks': clocks,
-        'module': os.path.relpath(kinetix.modulePath(), ROOT),
-        'host_binding': numa,
+        'module': os.path.relpath(module_path, ROOT),
+        'host_binding': b.numa,
+        'configs': configs,
     }
     if world == 1 and not args.no_cpu_baseline:
-        if all_cpus:
-            os.sched_setaffinity(0, all_cpus)      # the CPU baseline runs on ALL host cores, not the GPU-local ones
+        if b.all_cpus:
+            os.sched_setaffinity(0, b.all_cpus)      # the CPU baseline runs on ALL host cores, not the GPU-local ones
         try:
             line['cpu_baseline'] = cpu_baseline(args.mechanism)
         except Exception as e:     # the baseline is reported, never required for the product number
             line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'unavailable', 'sample': str(e)}
     print(json.dumps(line), file=real_stdout, flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if b.dist is not None:
+        b.dist.destroy_process_group()
     return 0
 
 

@@ -13,8 +13,13 @@
  *   - addressing: T/T_ref at state[id], mass fraction k at state[id + offsetT + k*offset]; results use
  *     the same layout (rates) or [k*offset + id] (rhoD, cp_i);
  *   - `pressure` arguments are NON-DIMENSIONAL (p / p_ref), exactly as in kinetix.hpp:65-94;
- *   - one mechanism per process, not re-entrant, launches are asynchronous on the given stream and
- *     the caller synchronises (the reference: default stream + device.finish()).
+ *   - one mechanism per DEVICE (the reference: per process), launches are asynchronous on the given stream
+ *     and the caller synchronises (the reference: default stream + device.finish()); see kx_select_device.
+ *
+ *   - temperature contract: the generated kernels are valid for T in [200, 6000] K (the emitter proves by interval
+ *     arithmetic that every exp() argument stays in range there and folds Troe terms that are exactly 0 or 1 on that
+ *     interval, kinetix_b200/core/emit_bk1.py T_VALID_LO/HI); outside it results may saturate differently from the
+ *     reference's libm.  The reference's NASA-7 data are fitted for 200/300-3500/6000 K anyway.
  *
  * Calling sequence (same as benchmark/src/bk.cpp:574-760):
  *   kx_init -> getters -> kx_build -> kx_thermodynamic_props / kx_production_rates /
@@ -23,6 +28,7 @@
 #ifndef KINETIX_B200_H
 #define KINETIX_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -54,6 +60,15 @@ typedef struct kx_options {
 /* kinetix::init (kinetix.hpp:17-35 / kinetix.cpp:523-599): load the mechanism, generate + compile
  * (or load from cache) its sm_100a module, make the getters valid. */
 int kx_init(const char* yaml_path, const kx_options* options);
+
+/* Several GPUs from one process (extension; the reference's state is file-static, one device per process,
+ * kinetix.cpp:21-65): every kx_init creates (or replaces) the context of options->device_id and makes it the calling
+ * thread's current context; kx_select_device(d) switches the calling thread to the context initialised on device d
+ * (error if none).  All other entry points act on the current context and launch on ITS device.  One host thread per
+ * GPU may call concurrently, each after its own kx_select_device / kx_init; kx_finalize releases the current
+ * context only.  kx_current_device() = device of the current context, -1 if none. */
+int kx_select_device(int device_id);
+int kx_current_device(void);
 
 /* Generate + compile the mechanism module into the cache if it is not there yet, WITHOUT touching CUDA
  * (safe to call before fork(); a multi-process launcher calls it once, like rank 0 running the generator
@@ -135,6 +150,10 @@ double kx_ref_pressure(void);
 double kx_ref_temperature(void);
 int kx_ref_mass_fractions(double* out);
 double kx_ref_mean_molecular_weight(void);
+
+/* FNV-1a-64 step over a byte string: the hash of the `.inputs` stamp the generator writes beside a cached module and
+ * kx_init re-checks (exported so that the Python generator and this library agree by construction). */
+uint64_t kx_fnv1a64(uint64_t h, const void* data, size_t n);
 
 /* diagnostics */
 const char* kx_last_error(void);

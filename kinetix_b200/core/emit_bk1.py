@@ -214,6 +214,10 @@ class BK1Emitter:
             return K(A)
         if Ta == 0 and b in (-2, -1, 1, 2):
             return {-2: f'{K(A)} * rcpT * rcpT', -1: f'{K(A)} * rcpT', 1: f'{K(A)} * T', 2: f'{K(A)} * T * T'}[b]
+        if not A > 0:
+            # the reference folds ln A too (reaction_rates.py:218-241) and fails on math.log; say why
+            raise SystemExit(f'kinetix_b200: pre-exponential factor A = {A} is not positive; negative-A (or zero) '
+                             f'Arrhenius terms are not supported (neither does the reference: it folds ln A)')
         lnA = math.log(A)
         if b == 0:
             lo, hi = _arg_range(lnA, 0, -Ta)
@@ -671,8 +675,13 @@ class BK1Emitter:
                 w(f'  const double e = {self.exp("g", glo, ghi)};')
                 put(self.eg_slot, 'eg', 'e')
                 if need_neg[k]:
-                    put(self.rg_slot, 'rg', 'kx_rcp(e)')
-                    self.stats['rcp'] += 1
+                    if _exp_fn(glo, ghi) == 'kx_exp_wide':
+                        # e may be inf or 0 here; the Newton reciprocal would turn that into NaN, a second full-range
+                        # exp saturates to 0 / inf the way the reference's single exp(sum nu g) does
+                        put(self.rg_slot, 'rg', self.exp('-g', -ghi, -glo))
+                    else:
+                        put(self.rg_slot, 'rg', 'kx_rcp(e)')
+                        self.stats['rcp'] += 1
             else:
                 put(self.rg_slot, 'rg', self.exp("-g", -ghi, -glo))
             w('}')
@@ -937,6 +946,9 @@ class BK1Emitter:
 
         pl = rx.plog
         n = len(pl)
+        if n == 1:                                   # a single tabulated pressure: no interpolation, one rate
+            w(f'    double kf = {ksum(pl[0][1])};')
+            return
         w('    double kf;')
         for i in range(n - 1):
             (p1, k1), (p2, k2) = pl[i], pl[i + 1]

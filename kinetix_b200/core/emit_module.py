@@ -527,6 +527,14 @@ static int kxm_set_smem(K kernel, size_t smem) {{
   if (smem <= 48 * 1024) return 0;
   return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }}
+// launch-time state is kept PER DEVICE (function attributes belong to a device's context, SM counts differ): one
+// process may drive several GPUs through kx_select_device (csrc/kx_host.cpp)
+#define KXM_MAX_DEVICES 64
+static int kxm_device() {{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < KXM_MAX_DEVICES ? dev : 0;
+}}
 ''')
     if sp:
         out.append(f'''
@@ -551,11 +559,12 @@ static int launch_bk1(long long n, long long offsetT, long long offset, double p
                       const void* state, void* rates, double Tref, const void* pfield, cudaStream_t stream) {{
   const int block = {opt['block_bk1']};
   const size_t smem = {bk1_smem};
-  static bool configured = false;
-  if (!configured) {{
+  static bool configured[KXM_MAX_DEVICES] = {{}};
+  const int dev = kxm_device();
+  if (!configured[dev]) {{
     if (int e = kxm_set_smem(kx_bk1_f64<false>, smem)) return e;
     if (int e = kxm_set_smem(kx_bk1_f64<true>, smem)) return e;
-    configured = true;
+    configured[dev] = true;
   }}
   const unsigned grid = (unsigned)((n + block - 1) / block);
   if (pfield)
@@ -583,12 +592,9 @@ static int launch_thermo(long long n, long long offsetT, long long offset, doubl
 ''')
     if has_bk2:
         persistent_grid = '''  {   // persistent CTAs: one per SM, each loops over batches of per_cta states
-    static int n_sm = 0;
-    if (!n_sm) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1002;
-    }
-    if (grid > (unsigned)n_sm) grid = (unsigned)n_sm;
+    static int n_sm[KXM_MAX_DEVICES] = {};
+    if (!n_sm[dev] && cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1002;
+    if (grid > (unsigned)n_sm[dev]) grid = (unsigned)n_sm[dev];
   }
 ''' if bk2_persistent else ''
         out.append(f'''
@@ -597,10 +603,11 @@ static int launch_bk2(long long n, long long offsetT, long long offset, double p
                       void* conductivity, void* viscosity, void* rhoD, double Tref, cudaStream_t stream) {{
   const int block = KX_BK2_BLOCK, per_cta = {bk2_states_per_cta};   // states per CTA
   const size_t smem = {bk2_smem};
-  static bool configured = false;
-  if (!configured) {{
+  static bool configured[KXM_MAX_DEVICES] = {{}};
+  const int dev = kxm_device();
+  if (!configured[dev]) {{
     if (int e = kxm_set_smem(kx_bk2<S>, smem)) return e;
-    configured = true;
+    configured[dev] = true;
   }}
   unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
 {persistent_grid}  kx_bk2<S><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,

@@ -17,6 +17,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -55,9 +58,21 @@ struct State {
   void* d_in[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   void* d_out[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   size_t in_bytes = 0, out_bytes = 0;
-} g;
+};
 
-std::string g_error;
+// One context per CUDA device.  The reference keeps ONE set of file-static globals (kinetix.cpp:21-65: one
+// mechanism, one device per process); here a process may drive several GPUs: kx_init(options.device_id = d) creates
+// (or replaces) the context of device d and makes it current for the calling thread; kx_select_device(d) switches.
+// Every other entry point works on the calling thread's current context (a thread that never selected one uses the
+// context of the last kx_init of the process).  Contexts are never freed, only reset, so the pointers stay valid.
+std::map<int, State*> g_contexts;
+std::mutex g_contexts_mutex;
+State g_none;                              // "not initialised": every field at its default
+State* g_default = &g_none;
+thread_local State* t_current = nullptr;
+inline State& ctx() { return *(t_current ? t_current : g_default); }
+
+thread_local std::string g_error;
 
 int fail(const std::string& msg, int code = 1)
 {
@@ -101,25 +116,90 @@ std::string stem_of(const std::string& path)
 
 void unload()
 {
+  State& c = ctx();
+  if (&c == &g_none) return;
+  if (c.module) cudaSetDevice(c.device_id);
   for (int s = 0; s < State::SLOTS; s++) {
-    if (g.d_in[s]) cudaFree(g.d_in[s]);
-    if (g.d_out[s]) cudaFree(g.d_out[s]);
-    if (g.streams[s]) cudaStreamDestroy(g.streams[s]);
+    if (c.d_in[s]) cudaFree(c.d_in[s]);
+    if (c.d_out[s]) cudaFree(c.d_out[s]);
+    if (c.streams[s]) cudaStreamDestroy(c.streams[s]);
   }
-  if (g.module) dlclose(g.module);
-  g = State();
+  if (c.module) dlclose(c.module);
+  c = State();
+}
+
+// make the context of `device` (created on demand) the calling thread's current one
+State& select_context(int device)
+{
+  std::lock_guard<std::mutex> lock(g_contexts_mutex);
+  State*& slot = g_contexts[device];
+  if (!slot) slot = new State();
+  t_current = slot;
+  g_default = slot;
+  return *slot;
+}
+
+// launches go to the context's device whatever device the calling thread had current (cudaGetDevice is a
+// thread-local read, a few ns)
+int ensure_device()
+{
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev == ctx().device_id) return 0;
+  cudaError_t e = cudaSetDevice(ctx().device_id);
+  return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <class F>
 bool resolve(F& f, const char* sym)
 {
-  f = (F)dlsym(g.module, sym);
+  f = (F)dlsym(ctx().module, sym);
   return f != nullptr;
 }
 
 // host-supplied module builder (kx_set_module_builder); process-wide like the reference's static `buildKernel`
 kx_build_module_fn g_builder = nullptr;
 void* g_builder_user = nullptr;
+
+uint64_t fnv1a64(uint64_t h, const unsigned char* p, size_t n)
+{
+  for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 0x100000001b3ull;
+  return h;
+}
+
+// `.inputs` of a cached module: "fnv <hex>", "pinned <0|1>", then one input name per line ("@mechanism/<file>" = the
+// caller's mechanism file, everything else relative to the directory that holds the package).  True when the
+// recorded hash equals the hash of those files as they are NOW.
+bool inputs_match(const std::string& dir, const std::string& pkg, const char* yaml_path, int& pinned)
+{
+  std::ifstream in(dir + "/.inputs");
+  if (!in) return false;
+  std::string key, hex, line;
+  if (!(in >> key >> hex) || key != "fnv") return false;
+  if (!(in >> key >> pinned) || key != "pinned") return false;
+  std::getline(in, line);
+  const std::string root = pkg.substr(0, pkg.find_last_of('/'));
+  uint64_t h = 0xcbf29ce484222325ull;
+  int n_files = 0;
+  while (std::getline(in, line)) {
+    if (line.empty()) continue;
+    std::string path;
+    if (line.rfind("@mechanism/", 0) == 0) {
+      if (line.substr(11) != std::string(yaml_path).substr(std::string(yaml_path).find_last_of('/') + 1)) return false;
+      path = yaml_path;
+    } else {
+      path = root + "/" + line;
+    }
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::string bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    h = fnv1a64(h, (const unsigned char*)line.data(), line.size());
+    h = fnv1a64(h, (const unsigned char*)bytes.data(), bytes.size());
+    n_files++;
+  }
+  char now[32];
+  snprintf(now, sizeof(now), "%016llx", (unsigned long long)h);
+  return n_files > 0 && hex == now;
+}
 
 // Locate the compiled module of (mechanism, options) in the cache, generating + compiling it first if it
 // is missing (cf. kinetix.cpp:655-699: generator through system(), cached by option hash).  No CUDA calls.
@@ -135,12 +215,28 @@ int prepare_module(const char* yaml_path, const kx_options& opt, std::string& li
   const std::string dir = cache + "/" + tag;
   lib = dir + "/libkx_mech.so";
 
-  if ((!exists(lib) || getenv("KINETIX_B200_REBUILD")) && g_builder) {
+  // A cached module is trusted only if the inputs it was generated from are the inputs of THIS call: `.inputs`
+  // (written by kinetix_b200/jit.py) holds an FNV-1a-64 over the mechanism file and the emitter / csrc sources; the
+  // reference hashes its generator command line the same way and regenerates on mismatch (kinetix.cpp:677-699).
+  // An edited mechanism, another mechanism with the same file name, or an updated emitter therefore regenerate.
+  int pinned = 0;
+  // a module without the stamp was not made by the built-in generator: with a builder hook installed its freshness is
+  // the hook's business (it is called only when the library is missing); without one the generator decides
+  const bool hook_owned = g_builder && !exists(dir + "/.inputs");
+  const bool fresh = exists(lib) && !getenv("KINETIX_B200_REBUILD") &&
+                     (hook_owned || inputs_match(dir, pkg, yaml_path, pinned));
+  if (fresh) return 0;
+  if (exists(lib) && pinned && !getenv("KINETIX_B200_REBUILD"))
+    return fail("kx_init: the cached module " + lib + " was built with explicit emitter options and its inputs have "
+                "changed; rebuild it with the tool that made it (the default generator cannot reproduce it)");
+  if (g_builder) {
     if (opt.verbose) fprintf(stderr, "[kinetix_b200] module builder hook -> %s\n", dir.c_str());
     const int rc = g_builder(yaml_path, &opt, dir.c_str(), g_builder_user);
     if (rc != 0) return fail("kx_init: the module builder hook returned " + std::to_string(rc) + " for " + dir);
     if (!exists(lib)) return fail("kx_init: the module builder hook did not produce " + lib);
-  } else if (!exists(lib) || getenv("KINETIX_B200_REBUILD")) {
+  } else {
+    // the generator re-checks its own SHA-256 stamp, takes the per-module lock (concurrent ranks serialise, the
+    // first one builds) and renames the finished library into place
     const char* py = getenv("KINETIX_B200_PYTHON") ? getenv("KINETIX_B200_PYTHON") : "python3";
     std::string parent = pkg.substr(0, pkg.find_last_of('/'));
     std::ostringstream cmd;
@@ -154,6 +250,7 @@ int prepare_module(const char* yaml_path, const kx_options& opt, std::string& li
     if (opt.nonsym_dij) cmd << " --nonsymDij";
     if (opt.fit_rcp_diff_coeffs) cmd << " --fit-rcpdiffcoeffs";
     if (opt.block_size > 0) cmd << " --block-size " << opt.block_size;
+    if (getenv("KINETIX_B200_REBUILD")) cmd << " --force";
     if (opt.verbose) fprintf(stderr, "[kinetix_b200] %s\n", cmd.str().c_str());
     if (system(cmd.str().c_str()) != 0 || !exists(lib))
       return fail("kx_init: error while running the code generator / nvcc: " + cmd.str());
@@ -166,7 +263,21 @@ int prepare_module(const char* yaml_path, const kx_options& opt, std::string& li
 extern "C" {
 
 const char* kx_last_error(void) { return g_error.c_str(); }
-const char* kx_module_path(void) { return g.module_path.c_str(); }
+
+uint64_t kx_fnv1a64(uint64_t h, const void* data, size_t n) { return fnv1a64(h, (const unsigned char*)data, n); }
+
+int kx_select_device(int device_id)
+{
+  std::lock_guard<std::mutex> lock(g_contexts_mutex);
+  auto it = g_contexts.find(device_id);
+  if (it == g_contexts.end() || !it->second->module)
+    return fail("kx_select_device: no mechanism has been initialised on device " + std::to_string(device_id));
+  t_current = it->second;
+  return 0;
+}
+
+int kx_current_device(void) { return ctx().module ? ctx().device_id : -1; }
+const char* kx_module_path(void) { return ctx().module_path.c_str(); }
 
 int kx_finalize(void)
 {
@@ -176,7 +287,6 @@ int kx_finalize(void)
 
 int kx_init(const char* yaml_path, const kx_options* opt_in)
 {
-  unload();
   if (!yaml_path) return fail("kx_init: yaml_path is NULL");
   kx_options opt;
   memset(&opt, 0, sizeof(opt));
@@ -192,15 +302,17 @@ int kx_init(const char* yaml_path, const kx_options* opt_in)
                 "backend for that)");
   if (opt.device_id < 0 || opt.device_id >= ndev) return fail("kx_init: device_id out of range");
   if ((ce = cudaSetDevice(opt.device_id)) != cudaSuccess) return cuda_fail("cudaSetDevice", ce);
-  g.device_id = opt.device_id;
-  g.single_precision = opt.single_precision != 0;
+  select_context(opt.device_id);
+  unload();                                  // re-initialising a device replaces its mechanism
+  ctx().device_id = opt.device_id;
+  ctx().single_precision = opt.single_precision != 0;
 
   std::string lib;
   if (int e = prepare_module(yaml_path, opt, lib)) return e;
 
-  g.module = dlopen(lib.c_str(), RTLD_NOW | RTLD_LOCAL);
-  if (!g.module) return fail(std::string("kx_init: dlopen failed: ") + dlerror());
-  g.module_path = lib;
+  ctx().module = dlopen(lib.c_str(), RTLD_NOW | RTLD_LOCAL);
+  if (!ctx().module) return fail(std::string("kx_init: dlopen failed: ") + dlerror());
+  ctx().module_path = lib;
 
   fn_int_t abi = nullptr, nsp = nullptr, nact = nullptr, nrx = nullptr;
   fn_str_t names = nullptr;
@@ -208,8 +320,8 @@ int kx_init(const char* yaml_path, const kx_options* opt_in)
   if (!resolve(abi, "kxm_abi_version") || !resolve(nsp, "kxm_n_species") ||
       !resolve(nact, "kxm_n_active_species") || !resolve(nrx, "kxm_n_reactions") ||
       !resolve(names, "kxm_species_names") || !resolve(masses, "kxm_molar_masses") ||
-      !resolve(g.rates, "kxm_production_rates") || !resolve(g.transport, "kxm_transport") ||
-      !resolve(g.thermo, "kxm_thermo")) {
+      !resolve(ctx().rates, "kxm_production_rates") || !resolve(ctx().transport, "kxm_transport") ||
+      !resolve(ctx().thermo, "kxm_thermo")) {
     unload();
     return fail("kx_init: " + lib + " does not export the kxm_* module interface");
   }
@@ -218,20 +330,20 @@ int kx_init(const char* yaml_path, const kx_options* opt_in)
     return fail("kx_init: module ABI version mismatch, remove the cached module " + lib);
   }
   fn_int_t msp = nullptr;
-  if (!resolve(msp, "kxm_single_precision") || (msp() != 0) != g.single_precision) {
+  if (!resolve(msp, "kxm_single_precision") || (msp() != 0) != ctx().single_precision) {
     unload();
     return fail("kx_init: cached module " + lib + " was generated for a different precision");
   }
   // equivalent of the reference's mech.okl query kernels (kinetix.cpp:352-403)
-  g.n_species = nsp();
-  g.n_active = nact();
-  g.n_reactions = nrx();
-  g.m_molar.resize(g.n_species);
-  masses(g.m_molar.data());
+  ctx().n_species = nsp();
+  ctx().n_active = nact();
+  ctx().n_reactions = nrx();
+  ctx().m_molar.resize(ctx().n_species);
+  masses(ctx().m_molar.data());
   std::istringstream is(names());
   std::string tok;
-  while (is >> tok) g.names.push_back(tok);
-  if ((int)g.names.size() != g.n_species) {
+  while (is >> tok) ctx().names.push_back(tok);
+  if ((int)ctx().names.size() != ctx().n_species) {
     unload();
     return fail("kx_init: species name table is inconsistent");
   }
@@ -257,19 +369,19 @@ int kx_set_module_builder(kx_build_module_fn builder, void* user)
   return 0;
 }
 
-int kx_is_initialized(void) { return g.built ? 1 : 0; }
+int kx_is_initialized(void) { return ctx().built ? 1 : 0; }
 
 int kx_build(double ref_pressure, double ref_temperature, const double* ref_mass_fractions, int /*transport*/)
 {
-  if (!g.module) return fail("kx_build: call kx_init first");
+  if (!ctx().module) return fail("kx_build: call kx_init first");
   if (!ref_mass_fractions) return fail("kx_build: ref_mass_fractions is NULL");
-  g.ref_pressure = ref_pressure;
-  g.ref_temperature = ref_temperature;
-  g.ref_mass_fractions.assign(ref_mass_fractions, ref_mass_fractions + g.n_species);
+  ctx().ref_pressure = ref_pressure;
+  ctx().ref_temperature = ref_temperature;
+  ctx().ref_mass_fractions.assign(ref_mass_fractions, ref_mass_fractions + ctx().n_species);
   double sum = 0.;
-  for (int k = 0; k < g.n_species; k++) sum += ref_mass_fractions[k] / g.m_molar[k];   // kinetix.cpp:625-630
-  g.ref_mean_molar_mass = 1. / sum;
-  g.built = true;
+  for (int k = 0; k < ctx().n_species; k++) sum += ref_mass_fractions[k] / ctx().m_molar[k];   // kinetix.cpp:625-630
+  ctx().ref_mean_molar_mass = 1. / sum;
+  ctx().built = true;
   return 0;
 }
 
@@ -278,14 +390,15 @@ int kx_build(double ref_pressure, double ref_temperature, const double* ref_mass
 static int check_dtype(const char* who, int dtype)
 {
   if (dtype == KX_DTYPE_F64) return 0;
-  if (dtype == KX_DTYPE_F32 && g.single_precision) return 0;
+  if (dtype == KX_DTYPE_F32 && ctx().single_precision) return 0;
   return fail(std::string(who) + (dtype == KX_DTYPE_F32
                                       ? ": FP32 buffers need kx_init with single_precision = 1"
                                       : ": unknown dtype"));
 }
 
-#define KX_REQUIRE_BUILT(name) \
-  if (!g.built) return fail(name ": kx_init/kx_build have not been called")
+#define KX_REQUIRE_BUILT(name)                                                          \
+  if (!ctx().built) return fail(name ": kx_init/kx_build have not been called");        \
+  if (int e_dev = ensure_device()) return cuda_fail(name ": cudaSetDevice", e_dev)
 
 int kx_production_rates(int64_t n_states, int64_t offsetT, int64_t offset, double pressure, const void* d_state,
                         void* d_rates, int dtype, void* stream)
@@ -294,9 +407,9 @@ int kx_production_rates(int64_t n_states, int64_t offsetT, int64_t offset, doubl
   if (n_states < 0) return fail("kx_production_rates: negative n_states");
   if (n_states && (!d_state || !d_rates)) return fail("kx_production_rates: NULL buffer");
   if (int e = check_dtype("kx_production_rates", dtype)) return e;
-  const double pressure_ = pressure * g.ref_pressure;          // kinetix.cpp:802-803
+  const double pressure_ = pressure * ctx().ref_pressure;          // kinetix.cpp:802-803
   const double pressure_R = pressure_ / R_GAS;
-  int e = g.rates(n_states, offsetT, offset, pressure_R, pressure_, d_state, d_rates, g.ref_temperature, nullptr,
+  int e = ctx().rates(n_states, offsetT, offset, pressure_R, pressure_, d_state, d_rates, ctx().ref_temperature, nullptr,
                   dtype, (cudaStream_t)stream);
   return e ? cuda_fail("kx_production_rates", e) : 0;
 }
@@ -311,8 +424,8 @@ int kx_production_rates_pfield(int64_t n_states, int64_t offsetT, int64_t offset
   if (n_states < 0) return fail("kx_production_rates_pfield: negative n_states");
   if (n_states && (!d_state || !d_rates || !d_pressure)) return fail("kx_production_rates_pfield: NULL buffer");
   if (int e = check_dtype("kx_production_rates_pfield", dtype)) return e;
-  int e = g.rates(n_states, offsetT, offset, g.ref_pressure / R_GAS, g.ref_pressure, d_state, d_rates,
-                  g.ref_temperature, d_pressure, dtype, (cudaStream_t)stream);
+  int e = ctx().rates(n_states, offsetT, offset, ctx().ref_pressure / R_GAS, ctx().ref_pressure, d_state, d_rates,
+                  ctx().ref_temperature, d_pressure, dtype, (cudaStream_t)stream);
   return e ? cuda_fail("kx_production_rates_pfield", e) : 0;
 }
 
@@ -327,8 +440,8 @@ int kx_mixture_avg_transport_props(int64_t n_states, int64_t offsetT, int64_t of
   if (int e = check_dtype("kx_mixture_avg_transport_props", dtype)) return e;
   // the reference passes the non-dimensional pressure straight through (kinetix.cpp:832-840); note the
   // kernel argument order conductivity, viscosity
-  int e = g.transport(n_states, offsetT, offset, pressure, d_state, d_conductivity, d_viscosity, d_rho_d,
-                      g.ref_temperature, dtype, (cudaStream_t)stream);
+  int e = ctx().transport(n_states, offsetT, offset, pressure, d_state, d_conductivity, d_viscosity, d_rho_d,
+                      ctx().ref_temperature, dtype, (cudaStream_t)stream);
   if (e == 1001) return fail("kx_mixture_avg_transport_props: module was generated without transport");
   return e ? cuda_fail("kx_mixture_avg_transport_props", e) : 0;
 }
@@ -340,8 +453,8 @@ int kx_thermodynamic_props(int64_t n_states, int64_t offsetT, int64_t offset, do
   if (n_states < 0) return fail("kx_thermodynamic_props: negative n_states");
   if (n_states && (!d_state || !d_rho || !d_cp_i || !d_rho_cp)) return fail("kx_thermodynamic_props: NULL buffer");
   if (int e = check_dtype("kx_thermodynamic_props", dtype)) return e;
-  const double pressure_R = pressure * g.ref_pressure / R_GAS;   // kinetix.cpp:858
-  int e = g.thermo(n_states, offsetT, offset, pressure_R, d_state, d_rho, d_cp_i, d_rho_cp, g.ref_temperature,
+  const double pressure_R = pressure * ctx().ref_pressure / R_GAS;   // kinetix.cpp:858
+  int e = ctx().thermo(n_states, offsetT, offset, pressure_R, d_state, d_rho, d_cp_i, d_rho_cp, ctx().ref_temperature,
                    nullptr, dtype, (cudaStream_t)stream);
   return e ? cuda_fail("kx_thermodynamic_props", e) : 0;
 }
@@ -356,8 +469,8 @@ int kx_thermodynamic_props_pfield(int64_t n_states, int64_t offsetT, int64_t off
   if (n_states && (!d_state || !d_rho || !d_cp_i || !d_rho_cp || !d_pressure))
     return fail("kx_thermodynamic_props_pfield: NULL buffer");
   if (int e = check_dtype("kx_thermodynamic_props_pfield", dtype)) return e;
-  int e = g.thermo(n_states, offsetT, offset, g.ref_pressure / R_GAS, d_state, d_rho, d_cp_i, d_rho_cp,
-                   g.ref_temperature, d_pressure, dtype, (cudaStream_t)stream);
+  int e = ctx().thermo(n_states, offsetT, offset, ctx().ref_pressure / R_GAS, d_state, d_rho, d_cp_i, d_rho_cp,
+                   ctx().ref_temperature, d_pressure, dtype, (cudaStream_t)stream);
   return e ? cuda_fail("kx_thermodynamic_props_pfield", e) : 0;
 }
 
@@ -383,27 +496,35 @@ int64_t host_chunk()
 int ensure_staging(size_t in_bytes, size_t out_bytes)
 {
   for (int s = 0; s < State::SLOTS; s++) {
-    if (!g.streams[s]) {
-      cudaError_t e = cudaStreamCreateWithFlags(&g.streams[s], cudaStreamNonBlocking);
+    if (!ctx().streams[s]) {
+      cudaError_t e = cudaStreamCreateWithFlags(&ctx().streams[s], cudaStreamNonBlocking);
       if (e != cudaSuccess) return cuda_fail("cudaStreamCreate", e);
     }
   }
-  if (in_bytes > g.in_bytes) {
+  // grow: free every slot first and forget the pointers, so that a failed cudaMalloc can never leave a freed
+  // pointer behind (a later, smaller request would reuse it and unload() would free it twice)
+  auto grow = [&](void** bufs, size_t& have, size_t want, const char* what) -> int {
+    if (want <= have) return 0;
     for (int s = 0; s < State::SLOTS; s++) {
-      if (g.d_in[s]) cudaFree(g.d_in[s]);
-      cudaError_t e = cudaMalloc(&g.d_in[s], in_bytes);
-      if (e != cudaSuccess) return cuda_fail("cudaMalloc(staging in)", e);
+      if (bufs[s]) cudaFree(bufs[s]);
+      bufs[s] = nullptr;
     }
-    g.in_bytes = in_bytes;
-  }
-  if (out_bytes > g.out_bytes) {
+    have = 0;
     for (int s = 0; s < State::SLOTS; s++) {
-      if (g.d_out[s]) cudaFree(g.d_out[s]);
-      cudaError_t e = cudaMalloc(&g.d_out[s], out_bytes);
-      if (e != cudaSuccess) return cuda_fail("cudaMalloc(staging out)", e);
+      cudaError_t e = cudaMalloc(&bufs[s], want);
+      if (e != cudaSuccess) {
+        for (int t = 0; t < State::SLOTS; t++) {
+          if (bufs[t]) cudaFree(bufs[t]);
+          bufs[t] = nullptr;
+        }
+        return cuda_fail(what, e);
+      }
     }
-    g.out_bytes = out_bytes;
-  }
+    have = want;
+    return 0;
+  };
+  if (int e = grow(ctx().d_in, ctx().in_bytes, in_bytes, "cudaMalloc(staging in)")) return e;
+  if (int e = grow(ctx().d_out, ctx().out_bytes, out_bytes, "cudaMalloc(staging out)")) return e;
   return 0;
 }
 
@@ -412,7 +533,7 @@ int ensure_staging(size_t in_bytes, size_t out_bytes)
 int drain(int status)
 {
   for (int s = 0; s < State::SLOTS; s++)
-    if (g.streams[s]) cudaStreamSynchronize(g.streams[s]);
+    if (ctx().streams[s]) cudaStreamSynchronize(ctx().streams[s]);
   return status;
 }
 
@@ -420,7 +541,7 @@ int drain(int status)
 cudaError_t upload_chunk(const double* h_state, int64_t s0, int64_t len, int64_t offsetT, int64_t offset,
                          double* d, cudaStream_t st)
 {
-  const int N = g.n_species;
+  const int N = ctx().n_species;
   cudaError_t e = cudaMemcpyAsync(d, h_state + s0, len * sizeof(double), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
   return cudaMemcpy2DAsync(d + len, len * sizeof(double), h_state + s0 + offsetT, offset * sizeof(double),
@@ -435,16 +556,16 @@ int kx_production_rates_host(int64_t n_states, int64_t offsetT, int64_t offset, 
   KX_REQUIRE_BUILT("kx_production_rates_host");
   if (n_states <= 0) return n_states == 0 ? 0 : fail("kx_production_rates_host: negative n_states");
   if (!h_state || !h_rates) return fail("kx_production_rates_host: NULL buffer");
-  const int N = g.n_species;
+  const int N = ctx().n_species;
   const int64_t chunk = std::min<int64_t>(CHUNK, n_states);
   const size_t slab = (size_t)(N + 1) * chunk * sizeof(double);
   if (int e = ensure_staging(slab, slab)) return e;
   int slot = 0;
   for (int64_t s0 = 0; s0 < n_states; s0 += chunk, slot = (slot + 1) % State::SLOTS) {
     const int64_t len = std::min<int64_t>(chunk, n_states - s0);
-    cudaStream_t st = g.streams[slot];
-    double* din = (double*)g.d_in[slot];
-    double* dout = (double*)g.d_out[slot];
+    cudaStream_t st = ctx().streams[slot];
+    double* din = (double*)ctx().d_in[slot];
+    double* dout = (double*)ctx().d_out[slot];
     cudaError_t e = upload_chunk(h_state, s0, len, offsetT, offset, din, st);
     if (e != cudaSuccess) return drain(cuda_fail("kx_production_rates_host: H2D", e));
     if (int r = kx_production_rates(len, len, len, pressure, din, dout, KX_DTYPE_F64, st)) return drain(r);
@@ -455,7 +576,7 @@ int kx_production_rates_host(int64_t n_states, int64_t offsetT, int64_t offset, 
     if (e != cudaSuccess) return drain(cuda_fail("kx_production_rates_host: D2H", e));
   }
   for (int s = 0; s < State::SLOTS; s++) {
-    cudaError_t e = cudaStreamSynchronize(g.streams[s]);
+    cudaError_t e = cudaStreamSynchronize(ctx().streams[s]);
     if (e != cudaSuccess) return cuda_fail("kx_production_rates_host: sync", e);
   }
   return 0;
@@ -469,16 +590,16 @@ int kx_mixture_avg_transport_props_host(int64_t n_states, int64_t offsetT, int64
   if (n_states <= 0) return n_states == 0 ? 0 : fail("kx_mixture_avg_transport_props_host: negative n_states");
   if (!h_state || !h_viscosity || !h_conductivity || !h_rho_d)
     return fail("kx_mixture_avg_transport_props_host: NULL buffer");
-  const int N = g.n_species;
+  const int N = ctx().n_species;
   const int64_t chunk = std::min<int64_t>(CHUNK, n_states);
   if (int e = ensure_staging((size_t)(N + 1) * chunk * sizeof(double), (size_t)(N + 2) * chunk * sizeof(double)))
     return e;
   int slot = 0;
   for (int64_t s0 = 0; s0 < n_states; s0 += chunk, slot = (slot + 1) % State::SLOTS) {
     const int64_t len = std::min<int64_t>(chunk, n_states - s0);
-    cudaStream_t st = g.streams[slot];
-    double* din = (double*)g.d_in[slot];
-    double* dout = (double*)g.d_out[slot];   // [viscosity | conductivity | rhoD rows]
+    cudaStream_t st = ctx().streams[slot];
+    double* din = (double*)ctx().d_in[slot];
+    double* dout = (double*)ctx().d_out[slot];   // [viscosity | conductivity | rhoD rows]
     cudaError_t e = upload_chunk(h_state, s0, len, offsetT, offset, din, st);
     if (e != cudaSuccess) return drain(cuda_fail("kx_mixture_avg_transport_props_host: H2D", e));
     if (int r = kx_mixture_avg_transport_props(len, len, len, pressure, din, dout, dout + len, dout + 2 * len,
@@ -493,7 +614,7 @@ int kx_mixture_avg_transport_props_host(int64_t n_states, int64_t offsetT, int64
     if (e != cudaSuccess) return drain(cuda_fail("kx_mixture_avg_transport_props_host: D2H", e));
   }
   for (int s = 0; s < State::SLOTS; s++) {
-    cudaError_t e = cudaStreamSynchronize(g.streams[s]);
+    cudaError_t e = cudaStreamSynchronize(ctx().streams[s]);
     if (e != cudaSuccess) return cuda_fail("kx_mixture_avg_transport_props_host: sync", e);
   }
   return 0;
@@ -509,16 +630,16 @@ int kx_rates_and_transport_host(int64_t n_states, int64_t offsetT, int64_t offse
   if (n_states <= 0) return n_states == 0 ? 0 : fail("kx_rates_and_transport_host: negative n_states");
   if (!h_state || !h_rates || !h_viscosity || !h_conductivity || !h_rho_d)
     return fail("kx_rates_and_transport_host: NULL buffer");
-  const int N = g.n_species;
+  const int N = ctx().n_species;
   const int64_t chunk = std::min<int64_t>(CHUNK, n_states);
   if (int e = ensure_staging((size_t)(N + 1) * chunk * sizeof(double), (size_t)(2 * N + 3) * chunk * sizeof(double)))
     return e;
   int slot = 0;
   for (int64_t s0 = 0; s0 < n_states; s0 += chunk, slot = (slot + 1) % State::SLOTS) {
     const int64_t len = std::min<int64_t>(chunk, n_states - s0);
-    cudaStream_t st = g.streams[slot];
-    double* din = (double*)g.d_in[slot];
-    double* drates = (double*)g.d_out[slot];                 // (N+1) x len
+    cudaStream_t st = ctx().streams[slot];
+    double* din = (double*)ctx().d_in[slot];
+    double* drates = (double*)ctx().d_out[slot];                 // (N+1) x len
     double* dtr = drates + (size_t)(N + 1) * len;            // [viscosity | conductivity | rhoD rows]
     cudaError_t e = upload_chunk(h_state, s0, len, offsetT, offset, din, st);
     if (e != cudaSuccess) return drain(cuda_fail("kx_rates_and_transport_host: H2D", e));
@@ -540,53 +661,53 @@ int kx_rates_and_transport_host(int64_t n_states, int64_t offsetT, int64_t offse
     if (e != cudaSuccess) return drain(cuda_fail("kx_rates_and_transport_host: D2H", e));
   }
   for (int s = 0; s < State::SLOTS; s++) {
-    cudaError_t e = cudaStreamSynchronize(g.streams[s]);
+    cudaError_t e = cudaStreamSynchronize(ctx().streams[s]);
     if (e != cudaSuccess) return cuda_fail("kx_rates_and_transport_host: sync", e);
   }
   return 0;
 }
 
 // ---- getters (kinetix.cpp:873-908) ----------------------------------------------------------------
-int kx_n_species(void) { return g.n_species; }
-int kx_n_active_species(void) { return g.n_active; }
-int kx_n_reactions(void) { return g.n_reactions; }
+int kx_n_species(void) { return ctx().n_species; }
+int kx_n_active_species(void) { return ctx().n_active; }
+int kx_n_reactions(void) { return ctx().n_reactions; }
 
 const char* kx_species_name(int k)
 {
-  if (k < 0 || k >= (int)g.names.size()) return nullptr;
-  return g.names[k].c_str();
+  if (k < 0 || k >= (int)ctx().names.size()) return nullptr;
+  return ctx().names[k].c_str();
 }
 
 int kx_species_index(const char* name)
 {
   if (!name) return -1;
-  for (size_t k = 0; k < g.names.size(); k++)
-    if (g.names[k] == name) return (int)k;
+  for (size_t k = 0; k < ctx().names.size(); k++)
+    if (ctx().names[k] == name) return (int)k;
   return -1;
 }
 
 int kx_molar_masses(double* out)
 {
-  if (!g.module) return fail("kx_molar_masses: call kx_init first");
-  std::copy(g.m_molar.begin(), g.m_molar.end(), out);
+  if (!ctx().module) return fail("kx_molar_masses: call kx_init first");
+  std::copy(ctx().m_molar.begin(), ctx().m_molar.end(), out);
   return 0;
 }
 
 int kx_molecular_weights(double* out)
 {
   KX_REQUIRE_BUILT("kx_molecular_weights");
-  for (int k = 0; k < g.n_species; k++) out[k] = g.m_molar[k] / g.ref_mean_molar_mass;   // kinetix.cpp:888-895
+  for (int k = 0; k < ctx().n_species; k++) out[k] = ctx().m_molar[k] / ctx().ref_mean_molar_mass;   // kinetix.cpp:888-895
   return 0;
 }
 
-double kx_ref_pressure(void) { return g.ref_pressure; }
-double kx_ref_temperature(void) { return g.ref_temperature; }
-double kx_ref_mean_molecular_weight(void) { return g.ref_mean_molar_mass; }
+double kx_ref_pressure(void) { return ctx().ref_pressure; }
+double kx_ref_temperature(void) { return ctx().ref_temperature; }
+double kx_ref_mean_molecular_weight(void) { return ctx().ref_mean_molar_mass; }
 
 int kx_ref_mass_fractions(double* out)
 {
   KX_REQUIRE_BUILT("kx_ref_mass_fractions");
-  std::copy(g.ref_mass_fractions.begin(), g.ref_mass_fractions.end(), out);
+  std::copy(ctx().ref_mass_fractions.begin(), ctx().ref_mass_fractions.end(), out);
   return 0;
 }
 

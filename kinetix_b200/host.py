@@ -68,6 +68,9 @@ def library():
         getattr(lib, f).restype = _dbl
     lib.kx_last_error.restype = ctypes.c_char_p
     lib.kx_module_path.restype = ctypes.c_char_p
+    lib.kx_select_device.argtypes = [_int]
+    lib.kx_fnv1a64.restype = ctypes.c_uint64
+    lib.kx_fnv1a64.argtypes = [ctypes.c_uint64, ctypes.c_char_p, ctypes.c_size_t]
     _lib = lib
     return lib
 
@@ -101,6 +104,16 @@ def _stream(stream):
 
 
 # ---- kinetix:: API -----------------------------------------------------------------------------------
+def selectDevice(device_id):
+    """extension (kx_select_device): make the context initialised on `device_id` the calling thread's current one;
+    the reference drives one device per process (kinetix.cpp:21-65)"""
+    _check(library().kx_select_device(int(device_id)), 'kinetix.selectDevice')
+
+
+def currentDevice():
+    return int(library().kx_current_device())
+
+
 def isInitialized():
     return bool(library().kx_is_initialized())
 

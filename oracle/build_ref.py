@@ -30,9 +30,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = '/root/reference'
 OUT = os.path.join(HERE, '_ref')
 
+# every shipped mechanism has its parity oracle (the unrolled -O2 build of EtOHKonnov takes ~5 min of g++, once)
 DEFAULT = [('gri30', 'parity'), ('gri30', 'serial'), ('gri30', 'fpmix'),
            ('LiDryer', 'parity'), ('LiDryer', 'serial'),
-           ('NH3Konnov_edit', 'parity'), ('chempolimi_edit', 'parity'), ('LiDryer', 'rcpdiff')]
+           ('NH3Konnov_edit', 'parity'), ('chempolimi_edit', 'parity'), ('LiDryer', 'rcpdiff'),
+           ('H2_Konnov', 'parity'), ('H2_new_mech', 'parity'), ('gri30-20', 'parity'), ('gri30-27', 'parity'),
+           ('gri30-35', 'parity'), ('heptaneLu88', 'parity'), ('EtOHKonnov', 'parity'), ('EtOHKonnov', 'serial')]
 
 COMMON_DEFS = [
     '-D__KINETIX_DEVICE__=', '-D__KINETIX_CONST__=const', "-D__KINETIX_INLINE__=static inline",

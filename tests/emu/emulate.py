@@ -97,7 +97,8 @@ def _math_header():
 
 def bk1_source(mech_name, options=None, single_precision=False):
     """BK1 part of the module text (constants, NASA table, kernel) + launch shape, as emit_module plans it"""
-    mech = load_mechanism(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech_name + '.yaml'))
+    path = mech_name if os.path.exists(mech_name) else os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech_name + '.yaml')
+    mech = load_mechanism(path)
     src, stats = emit_module(mech, None, dict(options or {}), single_precision=single_precision)
     bk1 = src[:src.index('kx_rcpM[')]
     bk1 = bk1[:bk1.rindex('\n')]                    # drop the started table line
@@ -160,7 +161,7 @@ extern "C" int emu_bk1(long long n, long long offsetT, long long offset, double 
                               open(os.path.join(HERE, 'kx_tm_emu.h')).read()).encode()).hexdigest()[:16]
         work = os.path.join(tempfile.gettempdir(), f'kx_emu_{os.getuid()}')
         os.makedirs(work, exist_ok=True)
-        lib = os.path.join(work, f'emu_{mech_name}{"_sp" if self.sp else ""}_{key}.so')
+        lib = os.path.join(work, f'emu_{os.path.basename(mech_name)}{"_sp" if self.sp else ""}_{key}.so')
         if not os.path.exists(lib):
             d = tempfile.mkdtemp(dir=work)
             with open(os.path.join(d, 'kx_math_emu.h'), 'w') as fh:

@@ -107,3 +107,51 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(('.py', '.cpp', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text and 'oracle/' not in text, f
+
+
+def test_cached_module_is_rechecked_against_its_inputs(tmp_path):
+    """kx_prepare / kx_init trust a cached module only while the mechanism file and the emitter sources it was
+    generated from are unchanged (the `.inputs` stamp; the reference hashes its generator command line and
+    regenerates on mismatch, kinetix.cpp:677-699): an edited mechanism, and a DIFFERENT mechanism under the same file
+    name in another directory, both regenerate; an identical copy elsewhere does not.  Two processes preparing the
+    same uncached module at once serialise on the cache lock and both succeed."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    import kinetix_b200.host as kinetix
+    cache = str(tmp_path / 'cache')
+    a = tmp_path / 'a'
+    b = tmp_path / 'b'
+    a.mkdir()
+    b.mkdir()
+    shutil.copyfile(mech_path('LiDryer'), a / 'mech.yaml')
+    lib = os.path.join(cache, 'mech', 'libkx_mech.so')
+    # two concurrent first builds
+    code = (f"import sys; sys.path.insert(0, {ROOT!r}); import kinetix_b200.host as k; "
+            f"k.prepare({str(a / 'mech.yaml')!r}, cache_dir={cache!r})")
+    procs = [subprocess.Popen([sys.executable, '-c', code]) for _ in range(2)]
+    assert [p.wait(timeout=600) for p in procs] == [0, 0]
+    assert os.path.exists(lib) and os.path.exists(os.path.join(cache, 'mech', '.inputs'))
+    assert not [f for f in os.listdir(os.path.join(cache, 'mech')) if '.tmp' in f]
+    t0 = os.stat(lib).st_mtime_ns
+    kinetix.prepare(str(a / 'mech.yaml'), cache_dir=cache)
+    assert os.stat(lib).st_mtime_ns == t0                       # fresh: nothing ran
+    shutil.copyfile(a / 'mech.yaml', b / 'mech.yaml')
+    kinetix.prepare(str(b / 'mech.yaml'), cache_dir=cache)
+    assert os.stat(lib).st_mtime_ns == t0                       # same contents elsewhere: still fresh
+    # a different mechanism under the same name
+    shutil.copyfile(mech_path('H2_Konnov'), b / 'mech.yaml')
+    kinetix.prepare(str(b / 'mech.yaml'), cache_dir=cache)
+    t1 = os.stat(lib).st_mtime_ns
+    assert t1 != t0
+    meta = json.load(open(os.path.join(cache, 'mech', 'mech.json')))
+    assert len(meta['mechanism']['species']) == 13              # H2_Konnov, not the 9-species LiDryer
+    # an edited mechanism (one pre-exponential factor)
+    text = open(a / 'mech.yaml').read()
+    assert '3.547e+15' in text
+    open(a / 'mech.yaml', 'w').write(text.replace('3.547e+15', '3.600e+15', 1))
+    kinetix.prepare(str(a / 'mech.yaml'), cache_dir=cache)
+    assert os.stat(lib).st_mtime_ns != t1
+    assert '3.6e+15' in open(os.path.join(cache, 'mech', 'kx_mech.cu')).read() or \
+        len(json.load(open(os.path.join(cache, 'mech', 'mech.json')))['mechanism']['species']) == 9

@@ -26,8 +26,8 @@ def _check(emu, orc, st, p, label):
 
 
 @pytest.mark.parametrize('mech,prefer_ref', [('LiDryer', True), ('gri30', True), ('NH3Konnov_edit', True),
-                                             ('H2_Konnov', False), ('H2_new_mech', False), ('gri30-20', False),
-                                             ('gri30-27', False), ('gri30-35', False), ('heptaneLu88', False)])
+                                             ('H2_Konnov', True), ('H2_new_mech', True), ('gri30-20', True),
+                                             ('gri30-27', True), ('gri30-35', True), ('heptaneLu88', True)])
 def test_generated_bk1_on_cpu(mech, prefer_ref):
     """every shipped mechanism (EtOHKonnov and chempolimi_edit have their own tests below), at 1 atm and at 30 bar"""
     emu = BK1Emulator(mech)
@@ -100,3 +100,45 @@ def test_generated_fp32_math_bk1_on_cpu(mech):
     rate_err, hrr_err = bk1_errors(new, ref)
     print(f'{mech} FP32-math kernel (emulated) vs FP64 oracle: rates {rate_err:.2e} hrr {hrr_err:.2e}')
     assert rate_err <= 1e-4 and hrr_err <= 5e-3
+
+
+def test_plog_with_a_single_tabulated_pressure(tmp_path):
+    """a P-log reaction with ONE rate entry has nothing to interpolate: the emitter writes its plain Arrhenius rate
+    (the text used to be invalid C for this case).  Checked against the same mechanism with that reaction turned into
+    an ordinary elementary reaction: identical results at any pressure."""
+    import os
+    from tests.common import mech_path
+    text = open(mech_path('chempolimi_edit')).read()
+    old = """  type: pressure-dependent-Arrhenius
+  rate-constants:
+  - {P: 0.1 atm, A: 9.2e+11, b: -0.01, Ea: 5039.4924}
+  - {P: 1.0 atm, A: 1.2e+12, b: -0.03, Ea: 5074.4662}
+  - {P: 10.0 atm, A: 4.7e+12, b: -0.2, Ea: 5344.4435}
+"""
+    assert old in text
+    one = tmp_path / 'plog1.yaml'
+    one.write_text(text.replace(old, """  type: pressure-dependent-Arrhenius
+  rate-constants:
+  - {P: 1.0 atm, A: 1.2e+12, b: -0.03, Ea: 5074.4662}
+"""))
+    plain = tmp_path / 'plain.yaml'
+    plain.write_text(text.replace(old, "  rate-constant: {A: 1.2e+12, b: -0.03, Ea: 5074.4662}\n"))
+    a, b = BK1Emulator(str(one)), BK1Emulator(str(plain))
+    st = synthetic_states(a.mech.n_species, 64, seed=2)
+    for p in (2.0e4, P_ATM, 5.0e6):
+        ra, rb = a.production_rates(st, p), b.production_rates(st, p)
+        assert np.isfinite(ra).all()
+        e_rate, e_hrr = bk1_errors(ra, rb)
+        assert e_rate <= 1e-13 and e_hrr <= 1e-12, (p, e_rate, e_hrr)
+
+
+def test_non_positive_pre_exponential_factor_is_rejected_with_a_message(tmp_path):
+    from kinetix_b200.core.emit_module import emit_module
+    from kinetix_b200.core.mechanism import load_mechanism
+    from tests.common import mech_path
+    text = open(mech_path('LiDryer')).read()
+    bad = tmp_path / 'negA.yaml'
+    bad.write_text(text.replace('A: 3.547e+15', 'A: -3.547e+15', 1))
+    with pytest.raises(SystemExit) as e:
+        emit_module(load_mechanism(str(bad)), None, {})
+    assert 'not positive' in str(e.value)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.common import Oracle, R, bk1_errors, mech_path, rel_err
+from tests.common import Oracle, R, bk1_errors, elementwise_errors, mech_path, rel_err
 from oracle.port import load_cantera_ci, synthetic_states
 
 torch = pytest.importorskip('torch')
@@ -63,8 +63,11 @@ def test_bk1_matches_oracle_on_random_states(kinetix, mech):
     ref = orc.production_rates(st, P_ATM)
     assert np.isfinite(new).all()
     rate_err, hrr_err = bk1_errors(new, ref)
-    print(f'{mech} BK1 vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}')
-    assert rate_err <= TOL and hrr_err <= TOL
+    e_all, e_sig = elementwise_errors(new, ref)
+    print(f'{mech} BK1 vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}; element-wise: all elements {e_all:.3e}, '
+          f'elements >= 1e-3 of their state\'s largest rate {e_sig:.3e}')
+    assert orc.kind == 'reference'
+    assert rate_err <= TOL and hrr_err <= TOL and e_sig <= TOL
 
 
 @pytest.mark.parametrize('mech', ['NH3Konnov_edit', 'chempolimi_edit'])
@@ -87,10 +90,12 @@ def test_bk1_plog_mechanisms_across_pressures(kinetix, mech):
 
 @pytest.mark.parametrize('mech', ['H2_Konnov', 'H2_new_mech', 'gri30-20', 'gri30-27', 'gri30-35', 'heptaneLu88'])
 def test_remaining_shipped_mechanisms(kinetix, mech):
-    """every mechanism shipped in kinetix/mechanisms goes through the emitter and matches the port
-    (the reference's stock kinetix_bk cannot even run the ones without a Pele directory)."""
+    """every mechanism shipped in kinetix/mechanisms goes through the emitter and matches the reference's own
+    generated code (oracle/_ref; the reference's stock kinetix_bk cannot even run the ones without a Pele
+    directory)."""
     N = _setup(kinetix, mech)
-    orc = Oracle(mech, prefer_ref=False)
+    orc = Oracle(mech)
+    assert orc.kind == 'reference'
     st = synthetic_states(N, 3000, seed=17)
     new = _run_bk1(kinetix, st, 1.0)
     ref = orc.production_rates(st, P_ATM)
@@ -103,22 +108,24 @@ def test_remaining_shipped_mechanisms(kinetix, mech):
 
 
 def test_largest_mechanism_etoh(kinetix):
-    """EtOHKonnov: 129 species / 1231 reactions incl. SRI falloff (BASELINE config 4); oracle = numpy port
-    (the reference's unrolled code needs 5 min of g++ for this mechanism)."""
+    """EtOHKonnov: 129 species / 1231 reactions incl. the only SRI falloff reactions of the shipped mechanisms
+    (reaction_rates.py:346-357; BASELINE config 4); oracle = the reference's own unrolled code (oracle/_ref)."""
     mech = 'EtOHKonnov'
     N = _setup(kinetix, mech)
     assert N == 129 and kinetix.nReactions() == 1231
-    orc = Oracle(mech, prefer_ref=False)
-    st = synthetic_states(N, 1500, seed=8)
+    orc = Oracle(mech)
+    assert orc.kind == 'reference'
+    st = synthetic_states(N, 6000, seed=8)
     new = _run_bk1(kinetix, st, 1.0)
     ref = orc.production_rates(st, P_ATM)
     rate_err, hrr_err = bk1_errors(new, ref)
-    print(f'{mech} BK1 vs port: rates {rate_err:.3e} hrr {hrr_err:.3e}')
-    assert rate_err <= TOL and hrr_err <= TOL
+    e_all, e_sig = elementwise_errors(new, ref)
+    print(f'{mech} BK1 vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}; element-wise all {e_all:.3e} significant {e_sig:.3e}')
+    assert rate_err <= TOL and hrr_err <= TOL and e_sig <= TOL
     cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
     rc, rv, rrd = orc.transport(st, 1.0)
     errs = rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)
-    print(f'{mech} BK2 vs port: {errs}')
+    print(f'{mech} BK2 vs {orc.kind}: {errs}')
     assert max(errs) <= TOL
 
 
@@ -134,12 +141,39 @@ def test_bk2_matches_oracle_on_random_states(kinetix, mech):
     assert max(errs) <= TOL
 
 
+def test_gri30_one_million_states_full_compare(kinetix):
+    """BASELINE configs 1 and 2 at their stated size: 1 Mi seeded GRI-3.0 states, EVERY output element of BK1 and
+    BK2 compared with the reference's own generated code (oracle/_ref on all host cores, ~20 s).  1 Mi states =
+    13.8 batches per persistent CTA of the default tensor-memory BK2 kernel (ring wrap, mbarrier phase flips, TMEM
+    reuse across batches) and 55 waves of BK1 CTAs."""
+    mech = 'gri30'
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech)
+    assert orc.kind == 'reference'
+    S = 1 << 20
+    st = synthetic_states(N, S, seed=20261017)
+    new = _run_bk1(kinetix, st, 1.0)
+    ref = orc.production_rates(st, P_ATM)
+    assert np.isfinite(new).all()
+    rate_err, hrr_err = bk1_errors(new, ref)
+    e_all, e_sig = elementwise_errors(new, ref)
+    print(f'{mech} BK1 {S} states vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}; element-wise all {e_all:.3e} significant {e_sig:.3e}')
+    assert rate_err <= TOL and hrr_err <= TOL and e_sig <= TOL
+    del new, ref
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    errs = rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)
+    print(f'{mech} BK2 {S} states vs {orc.kind}: cond {errs[0]:.3e} visc {errs[1]:.3e} rhoD {errs[2]:.3e} (element-wise)')
+    assert max(errs) <= TOL
+
+
 @pytest.mark.parametrize('variant', ['single', 'single_dense', 'lanes2', 'teams2', 'tmem_p1'])
 def test_bk2_kernel_variants_match_oracle(kinetix, variant):
     """the opt-in BK2 kernels (prebuilt by __graft_entry__.build() from the same emitter with different options:
     one state per thread with / without the low-rank Wilke factorisation, two lanes per state, the tensor-memory
     kernel with two teams / one state per thread) compute the same transport properties as the default kernel's
-    oracle; ragged size: several persistent-CTA rounds plus a partial batch."""
+    oracle; ragged size: 2.4 batches per persistent CTA of the tensor-memory kernels (148 SMs x 512 states x 2 + a
+    partial round + a partial batch), many waves of the one-state-per-thread kernels."""
     import __graft_entry__ as entry
     lib = os.path.join(entry.variant_dir(variant), 'libkx_mech.so')
     if not os.path.exists(lib):
@@ -149,7 +183,7 @@ def test_bk2_kernel_variants_match_oracle(kinetix, variant):
     N = kinetix.nSpecies()
     kinetix.build(P_ATM, 1.0, [1.0 / N] * N, True)
     orc = Oracle('gri30')
-    st = synthetic_states(N, 4 * 512 + 333, seed=99)
+    st = synthetic_states(N, 148 * 512 * 2 + 57 * 512 + 333, seed=99)
     cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
     rc, rv, rrd = orc.transport(st, 1.0)
     errs = rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)
@@ -171,9 +205,11 @@ def test_etoh_large_batch_is_replication_invariant(kinetix):
     assert np.isfinite(new).all()
     blocks = new.reshape(N + 1, reps, 1024)
     assert (blocks == blocks[:, :1, :]).all()
-    ref = Oracle(mech, prefer_ref=False).production_rates(base, P_ATM)
+    orc = Oracle(mech)
+    assert orc.kind == 'reference'
+    ref = orc.production_rates(base, P_ATM)
     rate_err, hrr_err = bk1_errors(np.ascontiguousarray(blocks[:, 0, :]), ref)
-    print(f'{mech} {st.shape[1]} states: replicas identical; first copy vs port: rates {rate_err:.3e} hrr {hrr_err:.3e}')
+    print(f'{mech} {st.shape[1]} states: replicas identical; first copy vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}')
     assert rate_err <= TOL and hrr_err <= TOL
 
 
@@ -442,7 +478,8 @@ def test_per_state_pressure_field(kinetix, mech):
     pressures straddle its P-log tables, so ln P is evaluated per state -- and a constant field must reproduce the
     scalar call (to rounding: p_ref/R * p instead of (p_ref * p)/R)."""
     N = _setup(kinetix, mech)
-    orc = Oracle(mech, prefer_ref=(mech == 'gri30'))
+    orc = Oracle(mech)
+    assert orc.kind == 'reference'
     S = 4000
     st = synthetic_states(N, S, seed=77)
     p_nd = np.array([0.3, 1.0, 7.0, 40.0])
