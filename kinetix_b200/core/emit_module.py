@@ -154,96 +154,8 @@ def _emit_bk2_single(out, mech, fits, opt, options, sp, rsize, tq):
     return bk2_smem, block2
 
 
-def choose_tile_lanes(N, lanes, forced=None):
-    """Tile edge (a multiple of `lanes`) minimising the pair slots evaluated per state: off-diagonal tiles are
-    full, a diagonal tile row i costs ceil(i / lanes) slots per lane."""
-    best = None
-    for tb in ([forced] if forced else (6, 8, 10, 12, 4)):
-        if tb % lanes:
-            continue
-        NP = -(-N // tb) * tb
-        NB = NP // tb
-        diag = sum(-(-i // lanes) for i in range(1, tb)) * lanes
-        slots = NB * (NB - 1) // 2 * tb * tb + NB * diag
-        cost = slots + 3 * NP * NP / 10.0          # + Wilke terms (3 DFMA vs ~10 per pair slot)
-        if best is None or cost < best[0] - 1e-9:
-            best = (cost, tb, NP)
-    return best[1], best[2]
-
-
-def _emit_bk2_lanes(out, mech, fits, opt, lanes, rsize, tq):
-    """Tables + macros for csrc/kx_bk2_lanes.cuh (`lanes` threads per state).  Returns (smem bytes, states per CTA)."""
-    N = mech.n_species
-    M = mech.molar_masses
-    tb, NP = choose_tile_lanes(N, lanes, opt.get('tile_bk2'))
-    NB = NP // tb
-    align = 16 // rsize
-    wchunk = -(-(NP * tb) // align) * align
-    dchunk = -(-(tb * tb * 6) // align) * align
-    cmax = max(wchunk, dchunk)
-    limit = 227 * 1024
-    max_threads = opt.get('bk2_max_threads', 512)
-    stages = opt.get('bk2_stages') or (4 if 4 * cmax * rsize <= 16 * 1024 else 2)
-
-    spt = opt.get('bk2_spt', 1)                    # states per lane group
-
-    def fit(stg):
-        states = (limit - 16 * stg - stg * cmax * rsize) // (2 * NP * rsize)
-        return min(states * lanes // spt, max_threads, 1024) // 32 * 32
-    threads = fit(stages)
-    if stages > 2 and fit(2) > threads and threads < max_threads:
-        stages, threads = 2, fit(2)                # the ring must not cost a warp
-    threads = opt.get('bk2_threads', threads)
-    states = threads // lanes * spt
-    smem = 16 * stages + (stages * cmax + 2 * NP * states) * rsize
-    out.append(f'#define KX_TB {tb}')
-    out.append(f'#define KX_NP {NP}')
-    out.append(f'#define KX_L {lanes}')
-    out.append(f'#define KX_P {spt}')
-    out.append(f'#define KX_BK2_BLOCK {threads}')
-    out.append(f'#define KX_STAGES {stages}')
-    out.append(f'#define KX_CHUNK_MAX {cmax}')
-    out.append(f'#define KX_WCHUNK {wchunk}')
-    out.append(f'#define KX_DCHUNK {dchunk}')
-    # one 16-real record per species: {1/M, M, M^-1/4, -, cond[0..4], -, visc[0..4], -}
-    sptab = []
-    for k in range(NP):
-        if k < N:
-            sptab += [1. / M[k], M[k], M[k] ** -0.25, 0.0] + list(fits.conductivity[k]) + [0.0] + list(fits.viscosity[k]) + [0.0]
-        else:
-            sptab += [0.0, 0.0, 1.0, 0.0] + [1.0, 0, 0, 0, 0, 0] + [1.0, 0, 0, 0, 0, 0]
-    out.append(_table('kx_sptab', sptab, qualifier='__device__ const __align__(16)'))
-    # Wilke mass factors c_kj = 1/sqrt(8 (1 + M_k/M_j)), one chunk per k-block: [kb][j][i], k = kb*tb + i, j < NP
-    wil = []
-    for kb in range(NB):
-        chunk = []
-        for j in range(NP):
-            for i in range(tb):
-                k = kb * tb + i
-                chunk.append(1.0 / math.sqrt(8.0 * (1.0 + M[k] / M[j])) if (k < N and j < N) else 0.0)
-        chunk += [0.0] * (wchunk - len(chunk))
-        wil += chunk
-    out.append(_table('kx_wilke', wil, qualifier='__device__ const __align__(16)'))
-    # binary diffusion quartics, lower-triangular tiles; padded pairs evaluate to D = 1
-    dif = []
-    for kb in range(NB):
-        for jb in range(kb + 1):
-            for i in range(tb):
-                for j in range(tb):
-                    k, jj = kb * tb + i, jb * tb + j
-                    if k < N and jj < N and k > jj:
-                        dif += list(fits.diffusivity[k][jj]) + [0.0]
-                    else:
-                        dif += [1.0, 0.0, 0.0, 0.0, 0.0, 0.0]
-            dif += [0.0] * (dchunk - tb * tb * 6)
-    out.append(f'#define KX_RCP_DIFF {1 if fits.reciprocal_diffusivity else 0}')
-    out.append(_table('kx_diff', dif, qualifier='__device__ const __align__(16)'))
-    out.append('#include "kx_bk2_lanes.cuh"')
-    return smem, states
-
-
 def _emit_bk2_tmem(out, mech, fits, opt, tq):
-    """Tables + macros for csrc/kx_bk2_tmem.cuh (persistent CTAs, two states per thread, S_k in tensor memory,
+    """Tables + macros for csrc/kx_bk2_tmem.cuh (persistent CTAs, KX_P states per thread, S_k in tensor memory,
     FP64).  Returns (smem bytes, states per CTA round, persistent=True) or None when the mechanism does not fit."""
     N = mech.n_species
     M = mech.molar_masses
@@ -252,7 +164,9 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     U, V, rank = wilke_low_rank(M)
     wr = rank + (rank & 1)
     limit = 227 * 1024
-    ns = -(-NP // 8) * 8                           # doubles reserved per state in tensor memory
+    # doubles per state in tensor memory: the row blocks run in descending order and the top block's sums are
+    # final (and consumed) before anything is stored, so only NB - 1 blocks ever live there
+    ns = max(NP - tb, 1)
     dchunk = tb * tb * 5
     cmax0 = max(dchunk, tb * (wr + 12))            # at least one species block per chunk of species rows
 
@@ -260,35 +174,35 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
         return tb * min(NB, max(1, cmax0 // (tb * width)))
     vrows, urows = rows(wr + 12), rows(wr + 6)
     cmax = -(-max(dchunk, vrows * (wr + 12), urows * (wr + 6)) // 2) * 2
-    # (threads, states per thread) in order of measured preference: 8 warps before 4, two states per thread (half
-    # the coefficient wavefronts per state) before one.  heptaneLu88 (88 species): 256 x 1 gives 236, 128 x 2 197 M
-    # states/s; EtOHKonnov (129 species) only fits 128 x 1 (97 vs 72 M for the shared-memory kernel).
-    plan = None
-    shapes = [(256, 2), (256, 1), (128, 2), (128, 1)]
-    if opt.get('bk2_spt'):
-        shapes = [sh for sh in shapes if sh[1] == opt['bk2_spt']]
-    for threads, spt in shapes:
-        if (threads // 128) * spt * 2 * ns > 512:  # columns per TMEM lane
-            continue
-        # two half-CTA teams with skewed phases were measured SLOWER (549 vs 608 M states/s on GRI-3.0): the teams
-        # run different parts of the ~120 KB unrolled body and miss the instruction cache (no_instruction stalls
-        # 4 % -> 18 %, profiles/ncu_r01_bk2_teams.txt); kept as an option
-        teams_opts = (opt['bk2_teams'],) if opt.get('bk2_teams') else (1,)
-        for teams in teams_opts:
+    # (threads, states per thread): as many resident states as shared memory (X_k: N doubles per state) and tensor
+    # memory (2 ns columns per state, ceil(warps / 4) x spt states per lane) allow; two states per thread (half the
+    # coefficient wavefronts per state) whenever that still leaves 8 warps.  Measured (M states/s): GRI-3.0 256 x 2:
+    # 644, 256 x 1: 469; heptaneLu88 256 x 1: 236, 128 x 2: 197; EtOHKonnov (129 species) 128 x 1: 97-103, and with the
+    # top block out of tensor memory 192 x 1 fits (two warps on lane quadrants 0 and 1).
+    plans = []
+    for spt in ((opt['bk2_spt'],) if opt.get('bk2_spt') else (2, 1)):
+        for threads in range(opt.get('bk2_max_threads', 256), 31, -32):
+            if opt.get('bk2_threads') and threads != opt['bk2_threads']:
+                continue
+            slots = -(-(threads // 32) // 4)
+            if slots * spt * 2 * (ns + 2) > 512:       # + 2 doubles per state: Mbar and sqrt(T) are parked there
+                continue
             for stages in ((opt['bk2_stages'],) if opt.get('bk2_stages') else (4, 2)):
-                smem = 16 * stages * teams + 16 + (teams * stages * cmax + N * threads * spt) * 8
+                smem = 16 * stages + 16 + (stages * cmax + N * threads * spt) * 8
                 if smem <= limit:
-                    plan = (threads, teams, stages, smem, spt)
+                    plans.append((threads, spt, stages, smem))
                     break
-            if plan:
-                break
-        if plan:
-            break
+            if plans and plans[-1][:2] == (threads, spt):
+                break                                  # largest CTA for this spt
+    plan = None
+    if plans:
+        # preference: 8 warps of two-state threads, else the most warps, then the most states
+        plan = max(plans, key=lambda pl: (pl[0] >= 256 and pl[1] == 2, pl[0], pl[0] * pl[1]))
     # small mechanisms are latency / bandwidth leaning and run faster as two 128-thread CTAs per SM of the
     # one-state-per-thread kernel (LiDryer 10.4 vs 7.9, gri30-20 2.96 vs 2.71 G states/s)
     if plan is None or plan[0] < opt.get('bk2_tmem_min_threads', 128) or N < opt.get('bk2_tmem_min_species', 25):
         return None
-    threads, teams, stages, smem, spt = plan
+    threads, spt, stages, smem = plan
     # every CTA allocates all 512 tensor-memory columns of its SM: never let two of them share an SM (the second
     # would wait in tcgen05.alloc until the first, persistent, CTA exits)
     smem = max(smem, 117 * 1024)
@@ -315,7 +229,7 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
                   for v in (([float(x) for x in U[k]] + [0.0] * (wr - rank) + list(fits.viscosity[k]) + [M[k] ** -0.25])
                             if k < N else [0.0] * wr + [1.0, 0, 0, 0, 0, 1.0]))
     nvc, nuc = -(-NP // vrows), -(-NP // urows)
-    for kb in range(NB):
+    for kb in range(NB - 1, -1, -1):                   # row blocks in the order the kernel walks them: descending
         for jb in range(kb + 1):
             tile = []
             for i in range(tb):
@@ -327,7 +241,6 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     out.append(f'#define KX_TB {tb}')
     out.append(f'#define KX_NP {NP}')
     out.append(f'#define KX_P {spt}')
-    out.append(f'#define KX_TEAMS {teams}')
     out.append(f'#define KX_NS {ns}')
     out.append(f'#define KX_BK2_BLOCK {threads}')
     out.append(f'#define KX_STAGES {stages}')
@@ -488,17 +401,12 @@ def emit_module(mech, fits, options=None, single_precision=False):
     if has_bk2:
         limit = 227 * 1024 - 1024
         align = 16 // rsize                            # chunk sizes are multiples of 16 bytes (bulk copy)
-        # lanes per state (csrc/kx_bk2_lanes.cuh): shared memory holds 2 NP reals per state, so large mechanisms
-        # get few resident states per SM; 2 or 4 lanes per state bring the resident warps back up
-        lanes = opt.get('bk2_lanes') or 1          # lanes > 1 measured slower on GRI-3.0 (profiles/): opt-in
         planned = None
-        if opt.get('bk2_tmem', True) and not sp and lanes == 1 and opt.get('bk2_spt', 2) in (1, 2) and not opt.get('bk2_ring'):
+        if opt.get('bk2_tmem', True) and not sp:
             planned = _emit_bk2_tmem(out, mech, fits, opt, tq)
         bk2_persistent = False
         if planned:
             bk2_smem, bk2_states_per_cta, bk2_persistent = planned
-        elif lanes > 1 or opt.get('bk2_spt', 1) > 1 or opt.get('bk2_ring'):
-            bk2_smem, bk2_states_per_cta = _emit_bk2_lanes(out, mech, fits, opt, lanes, rsize, tq)
         else:
             bk2_smem, bk2_states_per_cta = _emit_bk2_single(out, mech, fits, opt, options, sp, rsize, tq)
 

@@ -2,34 +2,31 @@
 // per-state sums S_k in TENSOR MEMORY, the mole fractions X_k in shared memory.  FP64 only.
 //
 // Same arithmetic as csrc/kx_bk2.cuh (reference benchmark/okl/transportProps.okl:11-49 around
-// kinetix/core/mix_transport.py:474-626).  What changed, and why (profiles/ncu_r01_bk2_*.txt):
+// kinetix/core/mix_transport.py:474-626).  Design, and why (profiles/ncu_r01_bk2_*.txt, ncu_r02_bk2_*.txt):
 //   * The one-state-per-thread kernel is bound by the shared-memory data pipe, not by the FP64 pipe: every
 //     species pair costs 3 LDS.128 (the quartic's coefficients, a broadcast) = 6 LSU wavefronts per warp against
-//     9 DFMA; in the pair loops the LSU pipe is the busier one (65 % of peak overall, FP64 58 %).  Replacing the
-//     coefficient loads by register moves (timing experiment) gave 739 instead of 446 M states/s.
-//   * So every coefficient fetched from shared memory is used for KX_P = 2 states here: half the wavefronts per
-//     state.  A thread then needs both states' vectors on chip, and shared memory (227 KB) only holds X_k AND
-//     S_k for 256 GRI-3.0 states per SM, i.e. 4 warps of two-state threads -- too few to cover latencies.
+//     9 DFMA.  So every coefficient fetched from shared memory is used for KX_P = 2 states here.
 //   * Blackwell's tensor memory is 256 KB per SM that this kernel would leave idle.  It is addressed as
 //     128 lanes x 512 32-bit columns, and warp w may touch lanes 32 (w % 4) .. +31: exactly a per-thread
-//     scratchpad.  The S_k of all 512 resident states live there (thread = lane, 2 * KX_NS columns per state,
-//     tcgen05.st / tcgen05.ld 32x32b, SASS STTM / LDTM), the X_k stay in shared memory as [k][state]: 8 warps
-//     of two-state threads per SM, and the S_k traffic (b_j in the Wilke sums, the read-modify-write of the
-//     column sums per tile) moves off the LSU pipe onto the otherwise unused TMEM datapath.
-//   * The Wilke sum uses a rank-KX_WR factorisation of its mass-factor matrix (see the Wilke section below):
-//     6 N r instead of 3 N^2 multiply-adds.
+//     scratchpad.  The running sums S_k live there (thread = lane, 2 * KX_NS columns per state,
+//     tcgen05.st / tcgen05.ld 32x32b, SASS STTM / LDTM), the X_k stay in shared memory as [k][state].
+//   * The Wilke sum uses a rank-KX_WR factorisation of its mass-factor matrix: 6 N r instead of 3 N^2 multiply-adds.
 //   * All tables (species quartics, Wilke factors, diffusion tiles) are ONE stream of chunks that goes through a
-//     KX_STAGES-deep ring of TMA bulk copies with full/empty mbarriers (no CTA-wide barrier per chunk, no
-//     constant-cache loads in the loops).
-//   * Persistent CTAs (one per SM) loop over batches of KX_BK2_BLOCK * KX_P states; tensor-memory allocation,
-//     barrier set-up and the ring's prefetch carry across batches.  KX_TEAMS = 2 splits the CTA into two
-//     independent half-CTA teams with skewed phases (measured slower: instruction-cache misses; off).
-//   * State rows are loaded in fully unrolled batches of 32 independent loads for all KX_P states.
+//     KX_STAGES-deep ring of TMA bulk copies with full/empty mbarriers.
+//   * Persistent CTAs (one per SM) loop over batches of KX_BK2_BLOCK * KX_P states.
+//   * Round 2: the row blocks of the pair loop run in DESCENDING order.  Block kb then receives its column
+//     contributions (from the blocks above it) BEFORE its own row pass, so its S_k are final when that pass ends:
+//     rho*D_km of the block is formed and stored right there, while the FP64 pipe works on the next block (the
+//     former epilogue -- reciprocals + N row stores at < 35 % pipe utilisation -- is gone), the top block never
+//     goes to tensor memory at all (KX_NS = KX_NP - KX_TB: a 129-species mechanism fits two warps per lane
+//     quadrant), and the X rows of a finished block are dead, so the NEXT batch's mass fractions are fetched into
+//     them with cp.async (LDGSTS) while this batch still computes: the next batch starts with a pass over shared
+//     memory instead of 2 x N dependent DRAM round trips (the former prologue).
 //
-// The including translation unit defines KX_N, KX_NP (multiple of KX_TB), KX_TB, KX_P, KX_TEAMS, KX_BK2_BLOCK
-// (threads; KX_BK2_BLOCK / KX_TEAMS a multiple of 128 so that a team's warps cover the four TMEM lane quadrants),
-// KX_NS (doubles reserved per state in TMEM, >= KX_NP), KX_STAGES, KX_CHUNK_MAX (reals per stage), KX_WR (even:
-// rank of the Wilke factorisation), the chunk layout KX_N_CHUNKS / KX_NVC / KX_NUC / KX_VROWS / KX_UROWS (below), KX_RCP_DIFF and the tables
+// The including translation unit defines KX_N, KX_NP (multiple of KX_TB), KX_TB, KX_P, KX_BK2_BLOCK (threads, a
+// multiple of 32: warp w uses TMEM lane quadrant w % 4, column slot w / 4), KX_NS (doubles per state in TMEM,
+// = KX_NP - KX_TB), KX_STAGES, KX_CHUNK_MAX (reals per stage), KX_WR (even: rank of the Wilke factorisation), the
+// chunk layout KX_N_CHUNKS / KX_NVC / KX_NUC / KX_VROWS / KX_UROWS (below), KX_RCP_DIFF and the tables
 //   __constant__ double kx_rcpM[KX_N], kx_M[KX_N]          1/M_k, M_k
 //   __constant__ int    kx_chunk_off[KX_N_CHUNKS + 1]      chunk boundaries in kx_bk2_stream (reals)
 //   __device__   double kx_bk2_stream[]                    the concatenated chunks, 16-byte aligned each
@@ -63,7 +60,7 @@ KX_DEVICE real kx_quartic(const real* __restrict__ c, real l, real l2, real l4)
 //   KX_NVC chunks of species rows, first pass (KX_VROWS rows x (12 + KX_WR): conductivity quartic, viscosity
 //          quartic, M^-1/4, -, row of the Wilke factor V)
 //   KX_NUC chunks of the Wilke factor U (KX_UROWS rows x (KX_WR + 6): U row, viscosity quartic, M^-1/4)
-//   the lower-triangular diffusion tiles (KX_TB^2 pairs x 5 coefficients), row-major over (kb, jb <= kb)
+//   the lower-triangular diffusion tiles (KX_TB^2 pairs x 5 coefficients): kb = KX_NB-1 .. 0, jb = 0 .. kb
 // Rows per chunk are multiples of KX_TB; padded species rows hold quartics = 1, M^-1/4 = 1, U = V = 0.
 KX_DEVICE const real* kx_chunk_src(int c) { return kx_bk2_stream + kx_chunk_off[c]; }
 KX_DEVICE unsigned kx_chunk_bytes(int c) { return (unsigned)((kx_chunk_off[c + 1] - kx_chunk_off[c]) * sizeof(real)); }
@@ -174,6 +171,14 @@ KX_DEVICE void kx_tm_store(unsigned taddr, const real (&d)[N])
   kx_tm_store_raw<N>(taddr, r);
 }
 
+// asynchronous 8-byte global -> shared copy (LDGSTS), no commit: the caller commits one group per row block
+KX_DEVICE void kx_cp_async8_nc(unsigned smem_addr, const void* gptr)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+KX_DEVICE void kx_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+KX_DEVICE void kx_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <typename ST>   // ST: storage type of the state / result buffers (reference: dfloat)
 __global__ void __launch_bounds__(KX_BK2_BLOCK, 1)
 kx_bk2(const long long n_states, const long long offsetT, const long long offset, const real pressure,
@@ -181,32 +186,31 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
        ST* __restrict__ rhoD, const double Tref)
 {
   extern __shared__ __align__(16) unsigned char kx_sm_raw[];
-  // PERSISTENT CTA of TEAMS independent teams of TT threads; a thread carries P states of its team's current
-  // batch (slots t, t + TT, ...): LDT = TT * P states per batch.  Each team has its own ring of table stages,
-  // so with two teams one team's memory-bound prologue / epilogue overlaps the other's FP64 loops (the second
-  // team starts half a batch late and the offset persists).
-  constexpr int P = KX_P, TEAMS = KX_TEAMS, TT = KX_BK2_BLOCK / TEAMS, LDT = TT * P, TB = KX_TB;
+  // PERSISTENT CTA of TT threads; a thread carries P states of the current batch (slots tt, tt + TT, ...):
+  // LDT = TT * P states per batch.
+  constexpr int P = KX_P, TT = KX_BK2_BLOCK, LDT = TT * P, TB = KX_TB, NB = KX_NB;
   constexpr int NWT = TT / 32, STG = KX_STAGES, R = KX_WR, RU = KX_WR + 6, RV = KX_WR + 12;
   constexpr int N_CHUNKS = KX_N_CHUNKS;
   constexpr int C_U = KX_NVC, C_D = C_U + KX_NUC;   // first chunk of U, of the tiles
-  constexpr int TM_COLS = (KX_BK2_BLOCK / 128) * P * 2 * KX_NS;         // columns in use per TMEM lane
-  static_assert((STG & (STG - 1)) == 0 && TT % 128 == 0 && TM_COLS <= 512 && KX_NS >= KX_NP, "shape");
+  constexpr int TM_SLOTS = (NWT + 3) / 4;                               // warps per TMEM lane quadrant
+  constexpr int TM_STATE = 2 * (KX_NS + 2);                             // columns per state: S_k, then Mbar and sqrt(T)/R
+  constexpr int TM_COLS = TM_SLOTS * P * TM_STATE;                      // columns in use per TMEM lane
+  static_assert((STG & (STG - 1)) == 0 && TT % 32 == 0 && TM_COLS <= 512 && KX_NS >= KX_NP - KX_TB, "shape");
   static_assert(C_D + KX_N_DTILES == N_CHUNKS, "chunk table");
-  const int team = threadIdx.x / TT, tt = threadIdx.x % TT, warp = threadIdx.x >> 5;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(kx_sm_raw);          // per team: STG full + STG empty
-  uint64_t* const full = bars + team * 2 * STG;
+  static_assert(sizeof(ST) == 8, "the tensor-memory BK2 kernel serves FP64 buffers");
+  const int tt = threadIdx.x, warp = threadIdx.x >> 5;
+  uint64_t* const full = reinterpret_cast<uint64_t*>(kx_sm_raw);          // STG full + STG empty barriers
   uint64_t* const empty = full + STG;
-  uint64_t* const skew = bars + TEAMS * 2 * STG;                          // one-time start signal for team 1
-  unsigned* const tm_base_slot = reinterpret_cast<unsigned*>(skew + 1);
-  real* const bufs = reinterpret_cast<real*>(kx_sm_raw + 16 * STG * TEAMS + 16);
-  real* const buf0 = bufs + team * STG * KX_CHUNK_MAX;                    // this team's STG stages
+  unsigned* const tm_base_slot = reinterpret_cast<unsigned*>(empty + STG);
+  real* const buf0 = reinterpret_cast<real*>(kx_sm_raw + 16 * STG + 16);  // STG stages of KX_CHUNK_MAX reals
   // X[k] of state p at X[k * LDT + p * TT]; only the KX_N real species have a row
-  real* __restrict__ X = bufs + TEAMS * STG * KX_CHUNK_MAX + team * (KX_N * LDT) + tt;
+  real* __restrict__ X = buf0 + STG * KX_CHUNK_MAX + tt;
+  const unsigned x_smem = kx_smem_addr(X);
   auto x_row = [&](int k) { return (k < KX_N ? k : KX_N - 1) * LDT; };
 
-  // batches of this team: b = blockIdx.x * TEAMS + team, + gridDim.x * TEAMS, ...
+  // batches of this CTA: blockIdx.x, + gridDim.x, ...
   const long long n_batches = (n_states + LDT - 1) / LDT;
-  const long long b_first = (long long)blockIdx.x * TEAMS + team, b_step = (long long)gridDim.x * TEAMS;
+  const long long b_first = (long long)blockIdx.x, b_step = (long long)gridDim.x;
   const long long my_batches = b_first < n_batches ? (n_batches - b_first + b_step - 1) / b_step : 0;
   const long long total_chunks = my_batches * N_CHUNKS;
 
@@ -218,112 +222,113 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   }
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < TEAMS * STG; s++) {
-      kx_mbar_init(&bars[(s / STG) * 2 * STG + s % STG], 1);
-      kx_mbar_init(&bars[(s / STG) * 2 * STG + STG + s % STG], NWT);
+    for (int s = 0; s < STG; s++) {
+      kx_mbar_init(&full[s], 1);
+      kx_mbar_init(&empty[s], NWT);
     }
-    kx_mbar_init(skew, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();   // mbarrier inits + TMEM base address visible
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // this thread's S_k of state p: lane quadrant (warp % 4), column (2 KX_NS) ((warp / 4) P + p) + 2 k
+  // this thread's S_k of state p: lane quadrant (warp % 4), column TM_STATE ((warp / 4) P + p) + 2 k
   const unsigned tm0 = *reinterpret_cast<volatile unsigned*>(tm_base_slot) + ((unsigned)(warp & 3) << 21) +
-                       (unsigned)((warp >> 2) * P * 2 * KX_NS);
-#define KX_TM(p, k) (tm0 + (unsigned)((p) * 2 * KX_NS + 2 * (k)))
+                       (unsigned)((warp >> 2) * P * TM_STATE);
+#define KX_TM(p, k) (tm0 + (unsigned)((p) * TM_STATE + 2 * (k)))
 
   if (tt == 0) {
 #pragma unroll
     for (int s = 0; s < STG; s++)
       if (s < total_chunks) kx_bulk_load(buf0 + s * KX_CHUNK_MAX, kx_chunk_src(s % N_CHUNKS), kx_chunk_bytes(s % N_CHUNKS), &full[s]);
-    if (TEAMS > 1 && team == 0 && my_batches == 0) kx_mbar_arrive(skew);
   }
-  if (TEAMS > 1 && team == 1 && my_batches > 0) kx_mbar_wait(skew, 0);
 
-  long long g = 0;   // chunks consumed so far by this team (all batches)
+  long long g = 0;   // chunks consumed so far by this CTA (all batches)
   auto acquire = [&]() -> const real* {
     kx_mbar_wait(&full[g & (STG - 1)], (unsigned)(g / STG) & 1);
     return buf0 + (g & (STG - 1)) * KX_CHUNK_MAX;
   };
-  // hand the stage back; the team's first thread refills it with the chunk STG ahead (possibly of the next batch)
+  // hand the stage back; the first thread refills it with the chunk STG ahead (possibly of the next batch)
   auto release = [&]() {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) kx_mbar_arrive(&empty[g & (STG - 1)]);
-    if (tt == 0) {
-      if (g + STG < total_chunks) {
-        const int s2 = (int)(g & (STG - 1)), c2 = (int)((g + STG) % N_CHUNKS);
-        kx_mbar_wait(&empty[s2], (unsigned)(g / STG) & 1);
-        kx_bulk_load(buf0 + s2 * KX_CHUNK_MAX, kx_chunk_src(c2), kx_chunk_bytes(c2), &full[s2]);
-      }
-      if (TEAMS > 1 && team == 0 && g == N_CHUNKS / 2) kx_mbar_arrive(skew);   // lets team 1 start, half a batch late
+    if (tt == 0 && g + STG < total_chunks) {
+      const int s2 = (int)(g & (STG - 1)), c2 = (int)((g + STG) % N_CHUNKS);
+      kx_mbar_wait(&empty[s2], (unsigned)(g / STG) & 1);
+      kx_bulk_load(buf0 + s2 * KX_CHUNK_MAX, kx_chunk_src(c2), kx_chunk_bytes(c2), &full[s2]);
     }
     g++;
   };
+  // state index of slot p of a batch (tail slots recompute the last state and store nothing)
+  // (the empty volatile asm pins the computation where it is written: hoisted above the Wilke passes as a loop
+  // invariant, the 64-bit indices and the pointers derived from them cost registers exactly where none are free)
+  auto state_id = [&](long long batch, int p) -> long long {
+    long long gid = batch * LDT + p * TT + tt;
+    asm volatile("" : "+l"(gid));
+    return gid < n_states ? gid : n_states - 1;
+  };
+  // fetch the mass fractions of species [k0, k1) of `batch` into this thread's own X slots (raw Y_k; they are
+  // turned into Y_k / M_k when that batch starts).  Nobody else reads or writes those slots.
+  auto prefetch_rows = [&](long long batch, int k0, int k1) {
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      const ST* src = state + state_id(batch, p) + offsetT;
+      for (int k = k0; k < k1; k++)
+        kx_cp_async8_nc(x_smem + (unsigned)((k * LDT + p * TT) * sizeof(real)), src + (size_t)k * offset);
+    }
+    kx_cp_async_commit();
+  };
+
+  if (b_first < n_batches) prefetch_rows(b_first, 0, KX_N);
 
 #pragma unroll 1
   for (long long batch = b_first; batch < n_batches; batch += b_step) {
-    bool live[P];
-    long long id[P];
-    real lnT[P], lnT2[P], lnT4[P], sqrT[P], Mbar[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const long long gid = batch * LDT + p * TT + tt;
-      live[p] = gid < n_states;
-      id[p] = live[p] ? gid : n_states - 1;   // tail slots recompute the last state, store nothing
-    }
+    const bool has_next = batch + b_step < n_batches;
+    real lnT[P], lnT2[P], lnT4[P], Mbar[P];
+    // (state indices are recomputed where they are needed instead of being held in registers across the pair loop)
+    auto is_live = [&](int p) { return batch * LDT + p * TT + tt < n_states; };
 
-    // ---- mole fractions (transportProps.okl:23-35): batches of 32 independent row loads for all P states ----
+    // ---- mole fractions (transportProps.okl:23-35): the rows were fetched into X while the previous batch was in
+    //      its pair loop; one pass over shared memory turns Y_k into Y_k / M_k and sums ----
     {
-      ST t_raw[P];
       real acc[P];
+      ST t_raw[P];
 #pragma unroll
-      for (int p = 0; p < P; p++) { t_raw[p] = kx_ld_stream(state + id[p]); acc[p] = 0; }
-      constexpr int LB = 32;
+      for (int p = 0; p < P; p++) {
+        acc[p] = 0;
+        t_raw[p] = kx_ld_stream(state + state_id(batch, p));   // L2 hit: prefetched during the previous batch
+      }
+      kx_cp_async_wait_all();
+#pragma unroll 8
+      for (int k = 0; k < KX_N; k++) {
 #pragma unroll
-      for (int k0 = 0; k0 < KX_N; k0 += LB) {
-        ST y[P][LB];
-#pragma unroll
-        for (int p = 0; p < P; p++)
-#pragma unroll
-          for (int i = 0; i < LB; i++)
-            if (k0 + i < KX_N) y[p][i] = kx_ld_stream(state + id[p] + offsetT + (size_t)(k0 + i) * offset);
-#pragma unroll
-        for (int p = 0; p < P; p++)
-#pragma unroll
-          for (int i = 0; i < LB; i++) {
-            if (k0 + i < KX_N) {
-              const real yi = (real)y[p][i];
-              const real w = (yi > (real)0 ? yi : (real)0) * kx_rcpM[k0 + i];
-              X[(k0 + i) * LDT + p * TT] = w;
-              acc[p] += w;
-            }
-          }
+        for (int p = 0; p < P; p++) {
+          const real yi = X[k * LDT + p * TT];
+          const real w = (yi > (real)0 ? yi : (real)0) * kx_rcpM[k];
+          X[k * LDT + p * TT] = w;
+          acc[p] += w;
+        }
       }
 #pragma unroll
       for (int p = 0; p < P; p++) {
         Mbar[p] = kx_rcp(acc[p]);
         const double Td = Tref * (double)t_raw[p];
         lnT[p] = (real)kx_log(Td);
-        sqrT[p] = kx_sqrt((real)Td);
         lnT2[p] = lnT[p] * lnT[p];
         lnT4[p] = lnT2[p] * lnT2[p];
+        // Mbar (after the first Wilke pass) and sqrt(T) are only needed where results are stored: parked in this
+        // thread's tensor-memory columns so that the loops have their registers (they run at the 255-register limit)
+        const real park[2] = {Mbar[p], kx_sqrt((real)Td)};
+        kx_tm_store<2>(KX_TM(p, KX_NS), park);
       }
-      // optional: pull the NEXT batch's state rows into L2 while this batch computes.  Measured slower (600 vs
-      // 610 M states/s on GRI-3.0: 108 extra LSU instructions per thread and batch), so off by default.
-#ifdef KX_L2_PREFETCH
-      if (batch + b_step < n_batches) {
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-          const long long nid = min((batch + b_step) * LDT + p * TT + tt, n_states - 1);
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(state + nid));
-#pragma unroll 4
-          for (int k = 0; k < KX_N; k++)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(state + nid + offsetT + (size_t)k * offset));
-        }
-      }
-#endif
     }
+    // sqrt(T) of state p, back from tensor memory
+    auto parked = [&](int p, real (&v)[2]) {
+      unsigned praw[4];
+      kx_tm_wait_st();
+      kx_tm_load<2>(KX_TM(p, KX_NS), praw);
+      kx_tm_wait_ld();
+      kx_tm_unpack<2>(praw, v);
+    };
 
     // ---- viscosity: Wilke, three matrix-vector products with a LOW-RANK mass-factor matrix ----
     //      (C1 + C2 v_k/v_j)^2 = c_kj (1 + w_k b_j)^2,  Phi_k = sum_j c_kj X_j (1 + 2 w_k b_j + w_k^2 b_j^2)
@@ -343,7 +348,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll 1
       for (int c = 0; c < KX_NVC; c++) {
         const real* __restrict__ cv = acquire();
-        const int jb1 = min(KX_NB, (c + 1) * (KX_VROWS / TB));
+        const int jb1 = min(NB, (c + 1) * (KX_VROWS / TB));
 #pragma unroll 1
         for (int jb = c * (KX_VROWS / TB); jb < jb1; jb++, cv += TB * RV) {
 #pragma unroll
@@ -381,8 +386,11 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         release();
       }
 #pragma unroll
-      for (int p = 0; p < P; p++)
-        if (live[p]) kx_st_stream(conductivity + id[p], (ST)(sqrT[p] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
+      for (int p = 0; p < P; p++) {
+        real pk[2];
+        parked(p, pk);
+        if (is_live(p)) kx_st_stream(conductivity + state_id(batch, p), (ST)(pk[1] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
+      }
 #pragma unroll
       for (int p = 0; p < P; p++)
 #pragma unroll
@@ -423,66 +431,110 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         release();
       }
 #pragma unroll
-      for (int p = 0; p < P; p++)
-        if (live[p]) kx_st_stream(viscosity + id[p], (ST)(sqrT[p] * vis[p]));
+      for (int p = 0; p < P; p++) {
+        real pk[2];
+        parked(p, pk);
+        if (is_live(p)) kx_st_stream(viscosity + state_id(batch, p), (ST)(pk[1] * vis[p]));
+      }
     }
 
-    // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj over tiles of the lower triangle; the
-    //      coefficients of a pair are fetched once for the P states ----
+    // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj over tiles of the lower triangle, row blocks
+    //      in DESCENDING order; the coefficients of a pair are fetched once for the P states.  When the row pass of
+    //      block kb ends its S_k are complete (the blocks above have already added their column contributions in
+    //      tensor memory): rho * D_km of the block is formed and stored at once (mix_transport.py:621-622 and
+    //      transportProps.okl:43-47; p and Mbar cancel), and the block's X rows are refilled with the next batch ----
+    if (has_next) {
+#pragma unroll
+      for (int p = 0; p < P; p++) asm volatile("prefetch.global.L2 [%0];" ::"l"(state + state_id(batch + b_step, p)));
+    }
+    {   // the column sums of blocks 0 .. NB-2 start from zero
+      const real zero[TB] = {};
 #pragma unroll 1
-    for (int kb = 0; kb < KX_NB; kb++) {
+      for (int jb = 0; jb < NB - 1; jb++)
+#pragma unroll
+        for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, jb * TB), zero);
+    }
+#pragma unroll 1
+    for (int kb = NB - 1; kb >= 0; kb--) {
+      const bool top = kb == NB - 1;          // the top block never goes to tensor memory: its sums start here
       real xk[P][TB], sk[P][TB];
-#pragma unroll
-      for (int p = 0; p < P; p++)
-#pragma unroll
-        for (int i = 0; i < TB; i++) {
-          const int k = kb * TB + i;
-          xk[p][i] = k < KX_N ? X[x_row(k) + p * TT] : (real)0;
-          sk[p][i] = 0;
-        }
-#pragma unroll 1
-      for (int jb = 0; jb < kb; jb++) {
-        real xj[P][TB], sj[P][TB];
+      {
         unsigned raw[P][2 * TB];
-        // running sums of the column block: requested from tensor memory now, unpacked when the tile has landed
-        kx_tm_wait_st();
+        if (!top) {
+          kx_tm_wait_st();
 #pragma unroll
-        for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, jb * TB), raw[p]);
+          for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, kb * TB), raw[p]);
+        }
 #pragma unroll
         for (int p = 0; p < P; p++)
 #pragma unroll
-          for (int i = 0; i < TB; i++) xj[p][i] = X[(jb * TB + i) * LDT + p * TT];   // jb < kb: real species
+          for (int i = 0; i < TB; i++) {
+            const int k = kb * TB + i;
+            xk[p][i] = k < KX_N ? X[x_row(k) + p * TT] : (real)0;
+          }
+        if (!top) {
+          kx_tm_wait_ld();
+#pragma unroll
+          for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], sk[p]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < P; p++)
+#pragma unroll
+            for (int i = 0; i < TB; i++) sk[p][i] = 0;
+        }
+      }
+#pragma unroll 1
+      for (int jb = 0; jb < kb; jb++) {
+        // One COLUMN j of the tile at a time: its mole fraction and running sum are scalars per state (fetched from
+        // shared / tensor memory one column ahead), only the row block's xk / sk stay in registers -- 64 registers
+        // fewer than holding the column block's vectors as well, which is what lets the block's final pass
+        // (rho*D_km) live in the same loop without spills.
+        unsigned raw[2][P][2];
+        real xj[P];
+        kx_tm_wait_st();
+#pragma unroll
+        for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB), raw[0][p]);
         const real* __restrict__ tile = acquire();
-        kx_tm_wait_ld();
 #pragma unroll
-        for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], sj[p]);
+        for (int j = 0; j < TB; j++) {
+          real sj[P];
 #pragma unroll
-        for (int i = 0; i < TB; i++) {
+          for (int p = 0; p < P; p++) xj[p] = X[(jb * TB + j) * LDT + p * TT];   // jb < kb: real species
+          kx_tm_wait_ld();
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            asm volatile("" : "+r"(raw[j & 1][p][0]), "+r"(raw[j & 1][p][1]));
+            sj[p] = __hiloint2double((int)raw[j & 1][p][1], (int)raw[j & 1][p][0]);
+          }
+          if (j + 1 < TB) {
+#pragma unroll
+            for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB + j + 1), raw[(j + 1) & 1][p]);
+          }
           real d[P][TB];
 #pragma unroll
-          for (int j = 0; j < TB; j++) {
+          for (int i = 0; i < TB; i++) {
             const real* cp = tile + (i * TB + j) * 5;
             const real c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
 #pragma unroll
             for (int p = 0; p < P; p++) {
               const real q = fma(c4, lnT4[p], fma(fma(c3, lnT[p], c2), lnT2[p], fma(c1, lnT[p], c0)));
-              d[p][j] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
+              d[p][i] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
             }
           }
 #pragma unroll
           for (int p = 0; p < P; p++) {
             real se = 0, so = 0;
 #pragma unroll
-            for (int j = 0; j < TB; j++) {
-              if (j & 1) so = fma(xj[p][j], d[p][j], so); else se = fma(xj[p][j], d[p][j], se);
-              sj[p][j] = fma(xk[p][i], d[p][j], sj[p][j]);
+            for (int i = 0; i < TB; i++) {
+              if (i & 1) so = fma(xk[p][i], d[p][i], so); else se = fma(xk[p][i], d[p][i], se);
+              sk[p][i] = fma(xj[p], d[p][i], sk[p][i]);
             }
-            sk[p][i] += se + so;
+            sj[p] += se + so;
+            unsigned w2[2] = {(unsigned)__double2loint(sj[p]), (unsigned)__double2hiint(sj[p])};
+            kx_tm_st2(KX_TM(p, jb * TB + j), w2);
           }
         }
         release();
-#pragma unroll
-        for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, jb * TB), sj[p]);
       }
       // diagonal tile: pairs i > j inside the block
       {
@@ -504,37 +556,34 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         }
         release();
       }
-      // first touch of this row block's sums (they replace b_k): later row blocks add their column contributions
+      // S_k of this block are final: rho * D_km = sqrt(T) / R * (Mbar - M_k X_k) / S_k, stored while the pipe goes on
+      unsigned praw[P][4];
+      kx_tm_wait_st();
 #pragma unroll
-      for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, kb * TB), sk[p]);
-    }
-    kx_tm_wait_st();
-
-    // ---- rho * D_km  (mix_transport.py:621-622 and transportProps.okl:43-47; p and Mbar cancel) ----
-#pragma unroll
-    for (int kb = 0; kb < KX_NB; kb++) {
-      unsigned raw[P][2 * TB];
-      real s[P][TB];
-#pragma unroll
-      for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, kb * TB), raw[p]);
+      for (int p = 0; p < P; p++) kx_tm_load<2>(KX_TM(p, KX_NS), praw[p]);
       kx_tm_wait_ld();
 #pragma unroll
-      for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], s[p]);
-#pragma unroll
       for (int p = 0; p < P; p++) {
-        const real f = sqrT[p] * (real)(1.0 / 8.31446261815324);      // rho*T^1.5/(p*Mbar) = sqrt(T)/R
+        real park[2];
+        kx_tm_unpack<2>(praw[p], park);
+        const real Mb = park[0], f = park[1] * (real)(1.0 / 8.31446261815324);   // rho*T^1.5/(p*Mbar) = sqrt(T)/R
+        const bool lv = is_live(p);
+        ST* const dst = rhoD + state_id(batch, p) + (size_t)(kb * TB) * offset;
 #pragma unroll
         for (int i = 0; i < TB; i++) {
           const int k = kb * TB + i;
           if (k < KX_N) {
-            const real num = fma(-kx_M[k], X[k * LDT + p * TT], Mbar[p]);
-            const real v = f * num * kx_rcp(s[p][i]);
-            if (live[p]) kx_st_stream(rhoD + id[p] + (size_t)k * offset, (ST)v);
+            const real num = fma(-kx_M[k], xk[p][i], Mb);
+            const real v = f * num * kx_rcp(sk[p][i]);
+            if (lv) kx_st_stream(dst + (size_t)i * offset, (ST)v);
           }
         }
       }
+      // the block's X rows are dead: the next batch's mass fractions move in
+      if (has_next) prefetch_rows(batch + b_step, kb * TB, min(KX_N, kb * TB + TB));
     }
   }
+  kx_cp_async_wait_all();
 
   // release tensor memory
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -167,11 +167,11 @@ def test_gri30_one_million_states_full_compare(kinetix):
     assert max(errs) <= TOL
 
 
-@pytest.mark.parametrize('variant', ['single', 'single_dense', 'lanes2', 'teams2', 'tmem_p1'])
+@pytest.mark.parametrize('variant', ['single', 'single_dense', 'tmem_p1'])
 def test_bk2_kernel_variants_match_oracle(kinetix, variant):
     """the opt-in BK2 kernels (prebuilt by __graft_entry__.build() from the same emitter with different options:
-    one state per thread with / without the low-rank Wilke factorisation, two lanes per state, the tensor-memory
-    kernel with two teams / one state per thread) compute the same transport properties as the default kernel's
+    one state per thread with / without the low-rank Wilke factorisation, the tensor-memory kernel with one state per
+    thread) compute the same transport properties as the default kernel's
     oracle; ragged size: 2.4 batches per persistent CTA of the tensor-memory kernels (148 SMs x 512 states x 2 + a
     partial round + a partial batch), many waves of the one-state-per-thread kernels."""
     import __graft_entry__ as entry
