@@ -558,6 +558,33 @@ def extra_configs(b, main, steps, warmup):
                 'partition': 'kinetix_b200.sharding.shard_of: contiguous ranges, remainder spread over the first ranks'})
     del state, bufs
     torch.cuda.empty_cache()
+    # what a single fused BK1+BK2 kernel could save at most: it would read the state slab once instead
+    # of twice.  Measured, not estimated: the thermo kernel streams exactly that slab (reads (N+1) rows, writes N+2) at
+    # HBM speed; its read share is the ceiling of the saving, and only if none of it were already hidden under FP64 work.
+    S = args.n_states
+    state = b.synthetic_states(N, S, seed_offset=9)
+    rho = torch.empty(S, dtype=torch.float64, device='cuda')
+    rcp = torch.empty_like(rho)
+    cp = torch.empty((N, S), dtype=torch.float64, device='cuda')
+    for _ in range(3):
+        k.thermodynamicProps(S, S, S, 1.0, state, rho, cp, rcp)
+    b.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        k.thermodynamicProps(S, S, S, 1.0, state, rho, cp, rcp)
+    e1.record()
+    b.barrier()
+    b.launches += steps
+    t_th = b.max_over_ranks([e0.elapsed_time(e1) / steps])[0]
+    read_share = (N + 1) / (2 * N + 3)
+    out.append({'name': 'fusion bound: state slab streamed once (thermo kernel, GRI-3.0, same states per GPU)',
+                'mechanism': 'gri30', 'states_per_gpu': S, 'thermo_ms': t_th,
+                'thermo_gb_per_s': (2 * N + 3) * 8 * S / (t_th * 1e-3) / 1e9,
+                'state_read_ms_upper_bound': t_th * read_share,
+                'note': 'a fused BK1+BK2 kernel saves at most state_read_ms_upper_bound per step (compare ms_per_step)'})
+    del state, rho, rcp, cp
+    torch.cuda.empty_cache()
     return out
 
 

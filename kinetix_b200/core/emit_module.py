@@ -317,6 +317,15 @@ def emit_module(mech, fits, options=None, single_precision=False):
             opt['minb_bk1'] = small
             bk1, bk1_src = emit_bk1()
     budget = 220 * 1024
+    # mid-size mechanisms whose live set does not fit the registers but whose scratch slots leave most of the shared
+    # memory idle (heptaneLu88: 41 live species, 29 slots): rarely used species keep C_k / wdot_k in shared-memory slots
+    # while they are live -- explicit placement of what ptxas would spill (spill loads 2.7 KB -> 0.6 KB per state,
+    # 652 -> 682 M states/s; EtOHKonnov, whose slots are already full, loses 6 %: not applied in the tensor-memory layout)
+    if (not sp and opt['gibbs_in_smem'] and 'cold_uses' not in (options or {})
+            and bk1.schedule_stats.get('peak_live', 0) > 30 and bk1.smem_doubles_per_thread <= 40
+            and bk1.smem_doubles_per_thread * 8 * 128 * 2 <= budget):
+        opt['cold_uses'], opt['cold_slot_cap'] = 40, 70
+        bk1, bk1_src = emit_bk1()
     # large mechanisms: when the scratch slots (exp(+-g_k) of live species, third-body sums) allow at most one
     # 128-thread CTA per SM in shared memory (EtOHKonnov: 210 slots), spread them over shared AND tensor memory
     # and run ONE 256-thread CTA per SM: twice the warps to hide latencies, and the (MB-sized) straight-line
@@ -499,13 +508,39 @@ static int launch_thermo(long long n, long long offsetT, long long offset, doubl
 }}
 ''')
     if has_bk2:
-        persistent_grid = '''  {   // persistent CTAs: one per SM, each loops over batches of per_cta states
-    static int n_sm[KXM_MAX_DEVICES] = {};
-    if (!n_sm[dev] && cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1002;
-    if (grid > (unsigned)n_sm[dev]) grid = (unsigned)n_sm[dev];
-  }
-''' if bk2_persistent else ''
-        out.append(f'''
+        if bk2_persistent:
+            out.append(f'''
+template <typename S>
+static int launch_bk2(long long n, long long offsetT, long long offset, double pressure, const void* state,
+                      void* conductivity, void* viscosity, void* rhoD, double Tref, cudaStream_t stream) {{
+  // persistent CTAs, one per SM, each loops over batches of KX_BK2_BLOCK x P states.  Launches with fewer than one
+  // full batch per SM use one state per thread: half-size batches, twice as many SMs at work.
+  const int block = KX_BK2_BLOCK;
+  const size_t smem = {bk2_smem};
+  static bool configured[KXM_MAX_DEVICES] = {{}};
+  static int n_sm[KXM_MAX_DEVICES] = {{}};
+  const int dev = kxm_device();
+  if (!configured[dev]) {{
+    if (int e = kxm_set_smem(kx_bk2<S, KX_P>, smem)) return e;
+    if (KX_P > 1) if (int e = kxm_set_smem(kx_bk2<S, 1>, smem)) return e;
+    if (cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1002;
+    configured[dev] = true;
+  }}
+  const bool small = KX_P > 1 && n <= (long long)n_sm[dev] * block * (KX_P - 1);
+  const int per_cta = block * (small ? 1 : KX_P);
+  unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
+  if (grid > (unsigned)n_sm[dev]) grid = (unsigned)n_sm[dev];
+  if (small)
+    kx_bk2<S, 1><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
+                                               (S*)viscosity, (S*)rhoD, Tref);
+  else
+    kx_bk2<S, KX_P><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
+                                                  (S*)viscosity, (S*)rhoD, Tref);
+  return (int)cudaGetLastError();
+}}
+''')
+        else:
+            out.append(f'''
 template <typename S>
 static int launch_bk2(long long n, long long offsetT, long long offset, double pressure, const void* state,
                       void* conductivity, void* viscosity, void* rhoD, double Tref, cudaStream_t stream) {{
@@ -517,8 +552,8 @@ static int launch_bk2(long long n, long long offsetT, long long offset, double p
     if (int e = kxm_set_smem(kx_bk2<S>, smem)) return e;
     configured[dev] = true;
   }}
-  unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
-{persistent_grid}  kx_bk2<S><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
+  const unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
+  kx_bk2<S><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
                                            (S*)viscosity, (S*)rhoD, Tref);
   return (int)cudaGetLastError();
 }}

@@ -179,7 +179,9 @@ KX_DEVICE void kx_cp_async8_nc(unsigned smem_addr, const void* gptr)
 KX_DEVICE void kx_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 KX_DEVICE void kx_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <typename ST>   // ST: storage type of the state / result buffers (reference: dfloat)
+// ST: storage type of the state / result buffers (reference: dfloat); P: states per thread -- KX_P for full batches,
+// 1 for small launches (fewer than one KX_P-state batch per SM: half-size batches put twice as many SMs to work)
+template <typename ST, int P>
 __global__ void __launch_bounds__(KX_BK2_BLOCK, 1)
 kx_bk2(const long long n_states, const long long offsetT, const long long offset, const real pressure,
        const ST* __restrict__ state, ST* __restrict__ conductivity, ST* __restrict__ viscosity,
@@ -188,7 +190,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   extern __shared__ __align__(16) unsigned char kx_sm_raw[];
   // PERSISTENT CTA of TT threads; a thread carries P states of the current batch (slots tt, tt + TT, ...):
   // LDT = TT * P states per batch.
-  constexpr int P = KX_P, TT = KX_BK2_BLOCK, LDT = TT * P, TB = KX_TB, NB = KX_NB;
+  constexpr int TT = KX_BK2_BLOCK, LDT = TT * P, TB = KX_TB, NB = KX_NB;
   constexpr int NWT = TT / 32, STG = KX_STAGES, R = KX_WR, RU = KX_WR + 6, RV = KX_WR + 12;
   constexpr int N_CHUNKS = KX_N_CHUNKS;
   constexpr int C_U = KX_NVC, C_D = C_U + KX_NUC;   // first chunk of U, of the tiles
@@ -278,7 +280,9 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
     kx_cp_async_commit();
   };
 
+#ifndef KX_BK2_NO_PREFETCH
   if (b_first < n_batches) prefetch_rows(b_first, 0, KX_N);
+#endif
 
 #pragma unroll 1
   for (long long batch = b_first; batch < n_batches; batch += b_step) {
@@ -297,7 +301,26 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         acc[p] = 0;
         t_raw[p] = kx_ld_stream(state + state_id(batch, p));   // L2 hit: prefetched during the previous batch
       }
+#ifdef KX_BK2_NO_PREFETCH
+      // development switch: the round-1 prologue (batches of 32 independent row loads straight from global memory)
+      constexpr int LB = 32;
+#pragma unroll
+      for (int k0 = 0; k0 < KX_N; k0 += LB) {
+        ST y[P][LB];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+#pragma unroll
+          for (int i = 0; i < LB; i++)
+            if (k0 + i < KX_N) y[p][i] = kx_ld_stream(state + state_id(batch, p) + offsetT + (size_t)(k0 + i) * offset);
+#pragma unroll
+        for (int p = 0; p < P; p++)
+#pragma unroll
+          for (int i = 0; i < LB; i++)
+            if (k0 + i < KX_N) X[(k0 + i) * LDT + p * TT] = (real)y[p][i];
+      }
+#else
       kx_cp_async_wait_all();
+#endif
 #pragma unroll 8
       for (int k = 0; k < KX_N; k++) {
 #pragma unroll
@@ -351,7 +374,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         const int jb1 = min(NB, (c + 1) * (KX_VROWS / TB));
 #pragma unroll 1
         for (int jb = c * (KX_VROWS / TB); jb < jb1; jb++, cv += TB * RV) {
-#pragma unroll
+#pragma unroll 1      // one species row per iteration: ~3 KB of code, resident in the L0 instruction cache
           for (int jj = 0; jj < TB; jj++) {
             const int j = jb * TB + jj;
             const real* row = cv + jj * RV;
@@ -485,35 +508,36 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
       }
 #pragma unroll 1
       for (int jb = 0; jb < kb; jb++) {
-        // One COLUMN j of the tile at a time: its mole fraction and running sum are scalars per state (fetched from
-        // shared / tensor memory one column ahead), only the row block's xk / sk stay in registers -- 64 registers
-        // fewer than holding the column block's vectors as well, which is what lets the block's final pass
-        // (rho*D_km) live in the same loop without spills.
-        unsigned raw[2][P][2];
-        real xj[P];
+        // One COLUMN j of the tile per iteration of a ROLLED loop: the column's mole fraction and running sum are
+        // scalars per state (shared / tensor memory, the sum fetched one column ahead), only the row block's xk / sk
+        // stay in registers.  The loop body is 9 pairs x P states = ~3 KB of code: it lives in the 6 KB L0
+        // instruction cache.  (Unrolled over the whole 9 x 9 tile the body is ~30 KB -- at the edge of the 32 KB
+        // L1.5 instruction cache: the round-1 body just fitted (hit rate 95 %), a few more instructions per pair
+        // and it thrashes: hit rate 77 %, no_instruction stalls x6, 434 instead of 644 M states/s.)
+        unsigned cur[P][2], nxt[P][2];
         kx_tm_wait_st();
 #pragma unroll
-        for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB), raw[0][p]);
+        for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB), cur[p]);
         const real* __restrict__ tile = acquire();
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < TB; j++) {
-          real sj[P];
+          real xj[P], sj[P];
 #pragma unroll
           for (int p = 0; p < P; p++) xj[p] = X[(jb * TB + j) * LDT + p * TT];   // jb < kb: real species
           kx_tm_wait_ld();
 #pragma unroll
           for (int p = 0; p < P; p++) {
-            asm volatile("" : "+r"(raw[j & 1][p][0]), "+r"(raw[j & 1][p][1]));
-            sj[p] = __hiloint2double((int)raw[j & 1][p][1], (int)raw[j & 1][p][0]);
+            asm volatile("" : "+r"(cur[p][0]), "+r"(cur[p][1]));
+            sj[p] = __hiloint2double((int)cur[p][1], (int)cur[p][0]);
           }
-          if (j + 1 < TB) {
+          // the next column's sum (the last iteration fetches one column past the tile: harmless, unused)
 #pragma unroll
-            for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB + j + 1), raw[(j + 1) & 1][p]);
-          }
+          for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB + min(j + 1, TB - 1)), nxt[p]);
           real d[P][TB];
+          const real* __restrict__ col = tile + j * 5;
 #pragma unroll
           for (int i = 0; i < TB; i++) {
-            const real* cp = tile + (i * TB + j) * 5;
+            const real* cp = col + i * TB * 5;
             const real c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
 #pragma unroll
             for (int p = 0; p < P; p++) {
@@ -532,8 +556,11 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
             sj[p] += se + so;
             unsigned w2[2] = {(unsigned)__double2loint(sj[p]), (unsigned)__double2hiint(sj[p])};
             kx_tm_st2(KX_TM(p, jb * TB + j), w2);
+            cur[p][0] = nxt[p][0];
+            cur[p][1] = nxt[p][1];
           }
         }
+        kx_tm_wait_ld();       // the look-ahead load of the last column
         release();
       }
       // diagonal tile: pairs i > j inside the block
@@ -580,7 +607,9 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         }
       }
       // the block's X rows are dead: the next batch's mass fractions move in
+#ifndef KX_BK2_NO_PREFETCH
       if (has_next) prefetch_rows(batch + b_step, kb * TB, min(KX_N, kb * TB + TB));
+#endif
     }
   }
   kx_cp_async_wait_all();

@@ -120,14 +120,11 @@ KX_DEVICE double kx_exp(double x)
 
 // exp(x) for arguments the emitter has PROVEN to lie in [-690, 690] for every valid state: no exponent
 // clamp at all (14 FP64 + 3 integer instructions).
-#ifdef KX_EXP_CALL
-// Experiment: ONE copy of the exp body, reached by CALL, instead of ~22 inlined instructions per use.  The BK1 kernels
-// are straight-line code of 0.26 (GRI-3.0) to 0.8 MB (EtOHKonnov) that is fetched once per CTA pass, and instruction
-// delivery, not the FP64 pipe, is what they wait for (no_instruction stalls); a third to a half of that text is exp.
-__device__ __noinline__ double kx_exp_nc(double x)
-#else
+// (Round 2 experiment: ONE copy of this body reached by CALL instead of ~22 inlined instructions per use shrinks the
+// straight-line BK1 text by 19-31 % and removes nearly all register spills, but executes ~20 % more instructions
+// (CALL/RET, argument moves, no scheduling across the call): GRI-3.0 958 vs 957 M states/s, heptaneLu88 467 vs 652,
+// EtOHKonnov 113 vs 164 -- rejected.)
 KX_DEVICE double kx_exp_nc(double x)
-#endif
 {
 #ifdef KX_EXP_TABLE
   return kx_exp_table_core(x, 0, 0, false);

@@ -46,10 +46,12 @@ def write_counts(module_dir):
     c = census(lib)
 
     def pick(fragment):
+        # several instantiations may match (BK2: full-batch and small-launch flavours): the largest is the main one
+        best = None
         for name, v in c.items():
-            if fragment in name:
-                return dict(v, kernel=name)
-        return None
+            if fragment in name and (best is None or v['total'] > best['total']):
+                best = dict(v, kernel=name)
+        return best
     counts = dict(source_sha256=source_hash(module_dir),
                   bk1=pick('kx_bk1_f64ILb0') or pick('kx_bk1_f32IdLb0'),
                   bk1_f32=pick('kx_bk1_f32IfLb0'),

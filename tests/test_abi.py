@@ -155,3 +155,12 @@ def test_cached_module_is_rechecked_against_its_inputs(tmp_path):
     assert os.stat(lib).st_mtime_ns != t1
     assert '3.6e+15' in open(os.path.join(cache, 'mech', 'kx_mech.cu')).read() or \
         len(json.load(open(os.path.join(cache, 'mech', 'mech.json')))['mechanism']['species']) == 9
+
+
+def test_select_device_needs_an_initialised_context(lib):
+    """kx_select_device switches the calling thread between per-device contexts; a device nothing was initialised
+    on is an error with a message, not a silent no-op"""
+    lib.kx_last_error.restype = ctypes.c_char_p
+    assert lib.kx_select_device(5) != 0
+    assert b'no mechanism has been initialised on device 5' in lib.kx_last_error()
+    assert lib.kx_current_device() in (-1, 0, 1, 2, 3, 4, 5, 6, 7)

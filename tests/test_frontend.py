@@ -156,16 +156,26 @@ def test_bk2_kernel_plan():
     src, _ = emit_module(m, fit_transport(m))
     d = _macros(src)
     assert '#include "kx_bk2_tmem.cuh"' in src and d['KX_P'] == 2 and d['KX_BK2_BLOCK'] == 256 and d['KX_WR'] == 12
-    assert (d['KX_BK2_BLOCK'] // 128) * d['KX_P'] * 2 * d['KX_NS'] <= 512
+    # tensor memory: ceil(warps / 4) x P states per lane, each KX_NS sums + 2 parked scalars; the top row block never
+    # goes to tensor memory (descending block order), so KX_NS = KX_NP - KX_TB
+    assert d['KX_NS'] == d['KX_NP'] - d['KX_TB']
+    assert -(-(d['KX_BK2_BLOCK'] // 32) // 4) * d['KX_P'] * 2 * (d['KX_NS'] + 2) <= 512
     offs = [int(x) for x in re.search(r'kx_chunk_off\[(\d+)\] = \{([^}]*)\}', src).group(2).split(',')]
     assert len(offs) == d['KX_N_CHUNKS'] + 1 and offs[0] == 0
     sizes = np.diff(offs)
     assert (sizes > 0).all() and (sizes % 2 == 0).all() and sizes.max() <= d['KX_CHUNK_MAX']
     n_tiles = (d['KX_NP'] // d['KX_TB']) * (d['KX_NP'] // d['KX_TB'] + 1) // 2
     assert d['KX_NVC'] + d['KX_NUC'] + n_tiles == d['KX_N_CHUNKS']
-    smem = int(re.search(r'per_cta = (\d+);.*\n  const size_t smem = (\d+);', src).group(2))
+    smem = int(re.search(r'const int block = KX_BK2_BLOCK;\n  const size_t smem = (\d+);', src).group(1))
     assert smem <= 227 * 1024
-    assert smem >= (d['KX_TEAMS'] * d['KX_STAGES'] * d['KX_CHUNK_MAX'] + 53 * 512) * 8
+    assert smem >= (d['KX_STAGES'] * d['KX_CHUNK_MAX'] + 53 * 512) * 8
+    # small launches run the one-state-per-thread instantiation of the same kernel
+    assert 'kx_bk2<S, 1><<<' in src and 'kx_bk2<S, KX_P><<<' in src
+    # the 129-species mechanism: 192 one-state threads (6 warps: lane quadrants 0 and 1 carry two warps)
+    m = mech('EtOHKonnov')
+    d = _macros(emit_module(m, fit_transport(m))[0])
+    assert d['KX_P'] == 1 and d['KX_BK2_BLOCK'] == 192 and 2 * 2 * (d['KX_NS'] + 2) <= 512
+    assert (129 * 192 + d['KX_STAGES'] * d['KX_CHUNK_MAX']) * 8 <= 227 * 1024
     # small mechanisms keep the one-state-per-thread kernel with the dense Wilke matrix
     m = mech('LiDryer')
     src, _ = emit_module(m, fit_transport(m))

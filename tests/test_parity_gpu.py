@@ -521,3 +521,32 @@ def test_errors_are_loud(kinetix):
         kinetix.init('/nonexistent/mech.yaml')
     with pytest.raises(kinetix.KinetixError):
         kinetix.init(mech_path('gri30'), tool='Pele')
+
+
+def test_two_devices_from_one_process(kinetix):
+    """per-device contexts (kx_select_device): one process initialises DIFFERENT mechanisms on two GPUs and
+    alternates between them; each launch lands on its context's device whatever device torch has current"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    mechs = {0: 'gri30', 1: 'LiDryer'}
+    for dev, mech in mechs.items():
+        kinetix.init(mech_path(mech), device_id=dev)
+        N = kinetix.nSpecies()
+        kinetix.build(P_ATM, 1.0, [1.0 / N] * N, True)
+    torch.cuda.set_device(0)
+    for dev in (1, 0, 1):
+        kinetix.selectDevice(dev)
+        assert kinetix.currentDevice() == dev
+        N = kinetix.nSpecies()
+        st = synthetic_states(N, 3000, seed=dev)
+        with torch.cuda.device(dev):
+            d_state = torch.from_numpy(st).cuda()
+            d_rates = torch.full_like(d_state, float('nan'))
+        kinetix.productionRates(3000, 3000, 3000, 1.0, d_state, d_rates, stream=0)
+        torch.cuda.synchronize(dev)
+        ref = Oracle(mechs[dev]).production_rates(st, P_ATM)
+        rate_err, hrr_err = bk1_errors(d_rates.cpu().numpy(), ref)
+        assert rate_err <= TOL and hrr_err <= TOL
+    for dev in (0, 1):
+        kinetix.selectDevice(dev)
+        kinetix.finalize()
