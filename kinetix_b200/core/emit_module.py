@@ -167,7 +167,11 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     # doubles per state in tensor memory: the row blocks run in descending order and the top block's sums are
     # final (and consumed) before anything is stored, so only NB - 1 blocks ever live there
     ns = max(NP - tb, 1)
-    dchunk = tb * tb * 5
+    # a diffusion tile is stored column by column, the rows of a column in PAIRS with their coefficients interleaved
+    # (c0(i), c0(i+1), c1(i), c1(i+1), ...): the kernel walks a tile one column at a time and fetches the coefficients
+    # of two pairs with five 16-byte loads (a 5-double record per pair would be 8-byte aligned every other pair)
+    col_size = (tb // 2) * 10 + (tb % 2) * 6
+    dchunk = tb * col_size
     cmax0 = max(dchunk, tb * (wr + 12))            # at least one species block per chunk of species rows
 
     def rows(width):
@@ -231,11 +235,18 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     nvc, nuc = -(-NP // vrows), -(-NP // urows)
     for kb in range(NB - 1, -1, -1):                   # row blocks in the order the kernel walks them: descending
         for jb in range(kb + 1):
+            def quartic(i, j):
+                k, jj = kb * tb + i, jb * tb + j
+                return list(fits.diffusivity[k][jj]) if (k < N and jj < N and k > jj) else [1.0, 0.0, 0.0, 0.0, 0.0]
             tile = []
-            for i in range(tb):
-                for j in range(tb):
-                    k, jj = kb * tb + i, jb * tb + j
-                    tile += list(fits.diffusivity[k][jj]) if (k < N and jj < N and k > jj) else [1.0, 0.0, 0.0, 0.0, 0.0]
+            for j in range(tb):
+                for i in range(0, tb - 1, 2):
+                    a, b2 = quartic(i, j), quartic(i + 1, j)
+                    for c in range(5):
+                        tile += [a[c], b2[c]]
+                if tb % 2:
+                    tile += quartic(tb - 1, j) + [0.0]
+            assert len(tile) == dchunk
             add_chunk(tile)
     n_chunks = len(offs) - 1
     out.append(f'#define KX_TB {tb}')
@@ -245,6 +256,7 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     out.append(f'#define KX_BK2_BLOCK {threads}')
     out.append(f'#define KX_STAGES {stages}')
     out.append(f'#define KX_CHUNK_MAX {cmax}')
+    out.append(f'#define KX_COL {col_size}')
     out.append(f'#define KX_WR {wr}')
     out.append(f'#define KX_VROWS {vrows}')
     out.append(f'#define KX_UROWS {urows}')

@@ -60,7 +60,8 @@ KX_DEVICE real kx_quartic(const real* __restrict__ c, real l, real l2, real l4)
 //   KX_NVC chunks of species rows, first pass (KX_VROWS rows x (12 + KX_WR): conductivity quartic, viscosity
 //          quartic, M^-1/4, -, row of the Wilke factor V)
 //   KX_NUC chunks of the Wilke factor U (KX_UROWS rows x (KX_WR + 6): U row, viscosity quartic, M^-1/4)
-//   the lower-triangular diffusion tiles (KX_TB^2 pairs x 5 coefficients): kb = KX_NB-1 .. 0, jb = 0 .. kb
+//   the lower-triangular diffusion tiles (KX_TB columns of KX_COL reals: the column's KX_TB quartics, rows paired and
+//          interleaved for 16-byte loads): kb = KX_NB-1 .. 0, jb = 0 .. kb
 // Rows per chunk are multiples of KX_TB; padded species rows hold quartics = 1, M^-1/4 = 1, U = V = 0.
 KX_DEVICE const real* kx_chunk_src(int c) { return kx_bk2_stream + kx_chunk_off[c]; }
 KX_DEVICE unsigned kx_chunk_bytes(int c) { return (unsigned)((kx_chunk_off[c + 1] - kx_chunk_off[c]) * sizeof(real)); }
@@ -534,15 +535,27 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll
           for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB + min(j + 1, TB - 1)), nxt[p]);
           real d[P][TB];
-          const real* __restrict__ col = tile + j * 5;
+          const real* __restrict__ col = tile + j * KX_COL;
 #pragma unroll
-          for (int i = 0; i < TB; i++) {
-            const real* cp = col + i * TB * 5;
-            const real c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
+          for (int i = 0; i + 1 < TB; i += 2) {      // two rows per record: five 16-byte loads
+            const real2* cp = reinterpret_cast<const real2*>(col + (i / 2) * 10);
+            const real2 c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
 #pragma unroll
             for (int p = 0; p < P; p++) {
-              const real q = fma(c4, lnT4[p], fma(fma(c3, lnT[p], c2), lnT2[p], fma(c1, lnT[p], c0)));
-              d[p][i] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
+              const real qa = fma(c4.x, lnT4[p], fma(fma(c3.x, lnT[p], c2.x), lnT2[p], fma(c1.x, lnT[p], c0.x)));
+              const real qb = fma(c4.y, lnT4[p], fma(fma(c3.y, lnT[p], c2.y), lnT2[p], fma(c1.y, lnT[p], c0.y)));
+              d[p][i] = KX_RCP_DIFF ? qa : KX_PAIR_RCP(qa);
+              d[p][i + 1] = KX_RCP_DIFF ? qb : KX_PAIR_RCP(qb);
+            }
+          }
+          if (TB & 1) {
+            const real* cp = col + (TB / 2) * 10;
+            const real2 c01 = *reinterpret_cast<const real2*>(cp), c23 = *reinterpret_cast<const real2*>(cp + 2);
+            const real c4 = cp[4];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+              const real q = fma(c4, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
+              d[p][TB - 1] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
             }
           }
 #pragma unroll
@@ -570,8 +583,11 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         for (int i = 1; i < TB; i++) {
 #pragma unroll
           for (int j = 0; j < i; j++) {
-            const real* cp = tile + (i * TB + j) * 5;
-            const real c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
+            // coefficient m of pair (i, j): paired rows interleaved, the odd last row on its own (see KX_COL)
+            const real* cp = tile + j * KX_COL + (i / 2) * 10 + ((i | 1) < TB ? (i & 1) : 0);
+            constexpr int CS = 2;
+            const int cs = (i | 1) < TB ? CS : 1;
+            const real c0 = cp[0], c1 = cp[cs], c2 = cp[2 * cs], c3 = cp[3 * cs], c4 = cp[4 * cs];
 #pragma unroll
             for (int p = 0; p < P; p++) {
               const real q = fma(c4, lnT4[p], fma(fma(c3, lnT[p], c2), lnT2[p], fma(c1, lnT[p], c0)));
