@@ -191,7 +191,8 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
             slots = -(-(threads // 32) // 4)
             if slots * spt * 2 * (ns + 2) > 512:       # + 2 doubles per state: Mbar and sqrt(T) are parked there
                 continue
-            for stages in ((opt['bk2_stages'],) if opt.get('bk2_stages') else (4, 2)):
+            # two stages of the coefficient ring are enough (GRI-3.0: 632 vs 616 M states/s with four)
+            for stages in ((opt['bk2_stages'],) if opt.get('bk2_stages') else (2,)):
                 smem = 16 * stages + 16 + (stages * cmax + N * threads * spt) * 8
                 if smem <= limit:
                     plans.append((threads, spt, stages, smem))
@@ -257,6 +258,11 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     out.append(f'#define KX_STAGES {stages}')
     out.append(f'#define KX_CHUNK_MAX {cmax}')
     out.append(f'#define KX_COL {col_size}')
+    # columns per iteration of the pair loop's body: one for two-state threads (3.5 KB of code, L0-resident; unrolling
+    # further measured no faster: GRI-3.0 633 / 629 / 589 M states/s for 1 / 3 / 9), more for one-state threads whose
+    # column is half the work (EtOHKonnov 5: 96.6 vs 91.5 M, heptaneLu88 8: 244 vs 232 M)
+    cu = opt.get('bk2_col_unroll') or (1 if spt == 2 else max(d for d in range(1, 9) if tb % d == 0))
+    out.append(f'#define KX_COL_UNROLL {cu}')
     out.append(f'#define KX_WR {wr}')
     out.append(f'#define KX_VROWS {vrows}')
     out.append(f'#define KX_UROWS {urows}')

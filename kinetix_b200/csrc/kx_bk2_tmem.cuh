@@ -47,6 +47,9 @@
 #define KX_PAIR_RCP kx_rcp_fast
 #endif
 #define KX_N_DTILES (KX_NB * (KX_NB + 1) / 2)
+#ifndef KX_COL_UNROLL
+#define KX_COL_UNROLL 1     // columns per iteration of the pair loop's body (1: ~3.5 KB of code, L0-resident)
+#endif
 static_assert(sizeof(real) == 8, "the tensor-memory BK2 kernel is FP64 only");
 
 // species quartic in ln T, Estrin form (dependency depth 3 instead of Horner's 4; these sit in the latency-bound
@@ -212,10 +215,12 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   auto x_row = [&](int k) { return (k < KX_N ? k : KX_N - 1) * LDT; };
 
   // batches of this CTA: blockIdx.x, + gridDim.x, ...
-  const long long n_batches = (n_states + LDT - 1) / LDT;
-  const long long b_first = (long long)blockIdx.x, b_step = (long long)gridDim.x;
-  const long long my_batches = b_first < n_batches ? (n_batches - b_first + b_step - 1) / b_step : 0;
-  const long long total_chunks = my_batches * N_CHUNKS;
+  // (32-bit counters: the pair loop runs at the 255-register limit, and the 64-bit batch / chunk counters were what
+  // ptxas spilled -- every reload on the critical path of a block's final pass, 10 % of the stall samples)
+  const int n_batches = (int)((n_states + LDT - 1) / LDT);
+  const int b_first = (int)blockIdx.x, b_step = (int)gridDim.x;
+  const int my_batches = b_first < n_batches ? (n_batches - b_first + b_step - 1) / b_step : 0;
+  const unsigned total_chunks = (unsigned)my_batches * N_CHUNKS;
 
   if (warp == 0) {
     // all 512 columns: this CTA is alone on its SM (shared memory), nobody else needs tensor memory
@@ -245,7 +250,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
       if (s < total_chunks) kx_bulk_load(buf0 + s * KX_CHUNK_MAX, kx_chunk_src(s % N_CHUNKS), kx_chunk_bytes(s % N_CHUNKS), &full[s]);
   }
 
-  long long g = 0;   // chunks consumed so far by this CTA (all batches)
+  unsigned g = 0;   // chunks consumed so far by this CTA (all batches)
   auto acquire = [&]() -> const real* {
     kx_mbar_wait(&full[g & (STG - 1)], (unsigned)(g / STG) & 1);
     return buf0 + (g & (STG - 1)) * KX_CHUNK_MAX;
@@ -262,16 +267,13 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
     g++;
   };
   // state index of slot p of a batch (tail slots recompute the last state and store nothing)
-  // (the empty volatile asm pins the computation where it is written: hoisted above the Wilke passes as a loop
-  // invariant, the 64-bit indices and the pointers derived from them cost registers exactly where none are free)
-  auto state_id = [&](long long batch, int p) -> long long {
-    long long gid = batch * LDT + p * TT + tt;
-    asm volatile("" : "+l"(gid));
+  auto state_id = [&](int batch, int p) -> long long {
+    const long long gid = (long long)batch * LDT + (p * TT + tt);
     return gid < n_states ? gid : n_states - 1;
   };
   // fetch the mass fractions of species [k0, k1) of `batch` into this thread's own X slots (raw Y_k; they are
   // turned into Y_k / M_k when that batch starts).  Nobody else reads or writes those slots.
-  auto prefetch_rows = [&](long long batch, int k0, int k1) {
+  auto prefetch_rows = [&](int batch, int k0, int k1) {
 #pragma unroll
     for (int p = 0; p < P; p++) {
       const ST* src = state + state_id(batch, p) + offsetT;
@@ -286,11 +288,11 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #endif
 
 #pragma unroll 1
-  for (long long batch = b_first; batch < n_batches; batch += b_step) {
+  for (int batch = b_first; batch < n_batches; batch += b_step) {
     const bool has_next = batch + b_step < n_batches;
     real lnT[P], lnT2[P], lnT4[P], Mbar[P];
     // (state indices are recomputed where they are needed instead of being held in registers across the pair loop)
-    auto is_live = [&](int p) { return batch * LDT + p * TT + tt < n_states; };
+    auto is_live = [&](int p) { return (long long)batch * LDT + (p * TT + tt) < n_states; };
 
     // ---- mole fractions (transportProps.okl:23-35): the rows were fetched into X while the previous batch was in
     //      its pair loop; one pass over shared memory turns Y_k into Y_k / M_k and sums ----
@@ -520,7 +522,8 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll
         for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB), cur[p]);
         const real* __restrict__ tile = acquire();
-#pragma unroll 1
+        constexpr int COL_UNROLL = KX_COL_UNROLL;
+#pragma unroll COL_UNROLL
         for (int j = 0; j < TB; j++) {
           real xj[P], sj[P];
 #pragma unroll
