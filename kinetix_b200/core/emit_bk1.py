@@ -573,7 +573,7 @@ class BK1Emitter:
         # ---- per-species live state --------------------------------------------------------------
         used = sorted(first)                                  # species that occur in some reaction
         # cold species: C_k / wdot_k in shared-memory slots while live (see cold_uses above)
-        mem_cs, mem_wd = {}, {}
+        mem_cs, mem_wd, seg_of = {}, {}, {}
         self.cold_activations = 0
 
         def CS(k):
@@ -582,12 +582,38 @@ class BK1Emitter:
         def WD(k):
             return f'gs[{mem_wd[k]} * {block}]' if k in mem_wd else f'wd{k}'
 
-        def place(k):
+        # Which live segments of which species keep C_k / wdot_k in shared-memory slots ("cold" placement): planned on
+        # the slot-usage timeline of the schedule, so that the slots EVER allocated stay within the cap (the CTA's
+        # shared memory, hence the CTAs per SM, must not change: GRI-3.0 with an in-use-only check grew from 63 to 79
+        # slots, lost its third CTA per SM and ran at 676 instead of 962 M states/s).  A species' exp(+-g) slots are
+        # busy from its activation to its retirement; a cold segment adds two more over the same span.
+        cold_plan = set()
+        if cold_uses and gibbs_in_smem and not tmem_slots:
+            n_pos = len(order)
+            usage = [len(eff_slot) + len([n for n in need_ln if eff_smem])] * (n_pos + 1)
+            for k, segs in segments.items():
+                for a, b in segs:
+                    for pos in range(a, b + 1):
+                        usage[pos] += int(need_pos[k]) + int(need_neg[k])
+            for k in sorted(segments, key=lambda k: segments[k][0][0]):
+                if len(uses[k]) > cold_uses:
+                    continue
+                for si, (a, b) in enumerate(segments[k]):
+                    if max(usage[a:b + 1]) + 2 <= cold_slot_cap:
+                        cold_plan.add((k, si))
+                        for pos in range(a, b + 1):
+                            usage[pos] += 2
+
+        def place(k, segment=0):
             """decide where species k lives for this live segment"""
             if not (cold_uses and gibbs_in_smem) or len(uses[k]) > cold_uses:
                 return
-            cap = smem_cap if tmem_slots else cold_slot_cap
-            if (n_slots - len(free_slots)) + 2 + 6 > cap:         # 6: head-room for exp(+-g) of the next activations
+            if tmem_slots:
+                # tensor-memory layout: shared-memory slots are capped by smem_cap, in-use check with head-room for the
+                # exp(+-g) of the next activations (the overflow goes to tensor memory, not to a bigger CTA)
+                if (n_slots - len(free_slots)) + 2 + 6 > smem_cap:
+                    return
+            elif (k, segment) not in cold_plan:
                 return
             a, b = take_slot(smem_only=True), take_slot(smem_only=True)
             if a is None or b is None:
@@ -623,7 +649,7 @@ class BK1Emitter:
 
         def activate(k, reactivation=False):
             """species k becomes live: concentration, zeroed accumulator, exp(+-g_k/RT)"""
-            place(k)
+            place(k, seg_of.get(k, 0))
             if routine:
                 w(f'{CS(k)} = Ci[{k}]; {WD(k)} = 0.0;')
             elif k in self.kept and not reactivation:
@@ -741,6 +767,7 @@ class BK1Emitter:
         for pos, ui in enumerate(order):
             members = units[ui]
             for k in sorted(by_first.get(pos, [])):
+                seg_of[k] = seg_index[(k, pos)]
                 if seg_index[(k, pos)] == 0:
                     issue_loads(rank[k] + prefetch)
                 else:                                   # re-activation after a suspension: fresh load
