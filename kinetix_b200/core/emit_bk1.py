@@ -309,7 +309,7 @@ class BK1Emitter:
     # ---- main --------------------------------------------------------------------------------
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
              reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False,
-             tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0, routine=False):
+             tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0, routine=False, kbase_ahead=0):
         """block / min_blocks: launch bounds.
         routine: emit the reference-signature DEVICE FUNCTION `kinetix_species_rates(lnT, T, T2, T3, T4, rcpT, P, lnP,
           Ci, wdot)` (reference reaction_rates.py:560-562) instead of the kernel: concentrations come from `Ci[]`,
@@ -764,8 +764,25 @@ class BK1Emitter:
 
         emitted = 0
         peak_live, live_now = 0, 0
+
+        def kbase_expr(pos):
+            rx0 = m.reactions[units[order[pos]][0]]
+            return None if rx0.kind == 'P-log' else self.arrhenius_group_expr(rx0.rate.A, rx0.rate.b, rx0.rate.Ta)
+
+        # kbase_ahead = A > 0: the rate constant of a unit depends on T only, so it is written A units BEFORE the unit
+        # that uses it -- its exp chain (16 dependent FP64 instructions) then sits next to independent arithmetic in
+        # the source, instead of relying on the scheduler to look that far (2 registers per constant in flight)
+        if kbase_ahead:
+            for pos in range(min(kbase_ahead, len(order))):
+                e = kbase_expr(pos)
+                if e is not None:
+                    w(f'double kb_{pos} = {e};')
         for pos, ui in enumerate(order):
             members = units[ui]
+            if kbase_ahead and pos + kbase_ahead < len(order):
+                e = kbase_expr(pos + kbase_ahead)
+                if e is not None:
+                    w(f'const double kb_{pos + kbase_ahead} = {e};')
             for k in sorted(by_first.get(pos, [])):
                 seg_of[k] = seg_index[(k, pos)]
                 if seg_index[(k, pos)] == 0:
@@ -782,8 +799,11 @@ class BK1Emitter:
             w(f'// ---- unit {pos}: reactions ' + ', '.join(str(i + 1) for i in members))
             w('{')
             if first_rx.kind != 'P-log':
-                w(f'  const double kbase = '
-                  f'{self.arrhenius_group_expr(first_rx.rate.A, first_rx.rate.b, first_rx.rate.Ta)};')
+                if kbase_ahead:
+                    w(f'  const double kbase = kb_{pos};')
+                else:
+                    w(f'  const double kbase = '
+                      f'{self.arrhenius_group_expr(first_rx.rate.A, first_rx.rate.b, first_rx.rate.Ta)};')
             for i in members:
                 rx = m.reactions[i]
                 w(f'  // {i + 1}: {rx.equation}')

@@ -319,7 +319,8 @@ def emit_module(mech, fits, options=None, single_precision=False):
         src = e.emit('kx_bk1_f64', opt['block_bk1'], opt['minb_bk1'], opt['sync_every'], opt['gibbs_in_smem'],
                      opt['reorder'], opt['prefetch'], opt['ring'], opt['pin_loads'], opt['l1_keep'], opt['keep_until'], opt['live_cap'], opt['eff_in_smem'], opt['nasa_indexed'],
                      tmem_slots=bk1_tm['slots'], smem_cap=bk1_tm['smem_cap'], tmem_cols=bk1_tm.get('cols', 512),
-                     cold_uses=opt.get('cold_uses', 0), cold_slot_cap=opt.get('cold_slot_cap', 0))
+                     cold_uses=opt.get('cold_uses', 0), cold_slot_cap=opt.get('cold_slot_cap', 0),
+                     kbase_ahead=opt.get('kbase_ahead', 0))
         return e, src
 
     bk1_tm = dict(slots=0, smem_cap=0)
