@@ -183,31 +183,39 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     # coefficient wavefronts per state) whenever that still leaves 8 warps.  Measured (M states/s): GRI-3.0 256 x 2:
     # 644, 256 x 1: 469; heptaneLu88 256 x 1: 236, 128 x 2: 197; EtOHKonnov (129 species) 128 x 1: 97-103, and with the
     # top block out of tensor memory 192 x 1 fits (two warps on lane quadrants 0 and 1).
+    # CTAs of 256 or 128 threads (whole warps per scheduler: 192 one-state threads measured no faster than 128 on
+    # EtOHKonnov, 98.4 vs 101.4 M states/s).  `lanes` = warps per state group: when only 128 one-state threads fit
+    # (EtOHKonnov: X_k alone is 1 KB per state), 256 threads work as two halves that SHARE the 128 states -- warps w
+    # and w + 4 own the same TMEM lanes and the same X_k -- and split every loop over species between them.
+    nx = max(3 * wr + 2, tb)                        # doubles one half hands to the other at a time
     plans = []
     for spt in ((opt['bk2_spt'],) if opt.get('bk2_spt') else (2, 1)):
-        for threads in range(opt.get('bk2_max_threads', 256), 31, -32):
+        for threads, lanes in ((256, 1), (256, 2), (128, 1)):
             if opt.get('bk2_threads') and threads != opt['bk2_threads']:
                 continue
-            slots = -(-(threads // 32) // 4)
-            if slots * spt * 2 * (ns + 2) > 512:       # + 2 doubles per state: Mbar and sqrt(T) are parked there
+            if opt.get('bk2_lanes') and lanes != opt['bk2_lanes']:
                 continue
+            if lanes == 2 and (spt != 1 or tb % 2 or not opt.get('bk2_split_warps', True)):
+                continue
+            states = threads // lanes * spt
+            slots = -(-(threads // lanes // 32) // 4)
+            if slots * spt * 2 * (ns + 2 + (lanes * nx if lanes > 1 else 0)) > 512:
+                continue                               # + 2 doubles per state: Mbar and sqrt(T) are parked there
             # two stages of the coefficient ring are enough (GRI-3.0: 632 vs 616 M states/s with four)
             for stages in ((opt['bk2_stages'],) if opt.get('bk2_stages') else (2,)):
-                smem = 16 * stages + 16 + (stages * cmax + N * threads * spt) * 8
+                smem = 16 * stages + 16 + (stages * cmax + N * states) * 8
                 if smem <= limit:
-                    plans.append((threads, spt, stages, smem))
+                    plans.append((threads, spt, stages, smem, lanes))
                     break
-            if plans and plans[-1][:2] == (threads, spt):
-                break                                  # largest CTA for this spt
     plan = None
     if plans:
-        # preference: 8 warps of two-state threads, else the most warps, then the most states
-        plan = max(plans, key=lambda pl: (pl[0] >= 256 and pl[1] == 2, pl[0], pl[0] * pl[1]))
+        # preference: the most resident states, then the most warps (256 x 2 > 256 x 1 > 256 as two halves > 128 x 1)
+        plan = max(plans, key=lambda pl: (pl[0] // pl[4] * pl[1], pl[0]))
     # small mechanisms are latency / bandwidth leaning and run faster as two 128-thread CTAs per SM of the
     # one-state-per-thread kernel (LiDryer 10.4 vs 7.9, gri30-20 2.96 vs 2.71 G states/s)
     if plan is None or plan[0] < opt.get('bk2_tmem_min_threads', 128) or N < opt.get('bk2_tmem_min_species', 25):
         return None
-    threads, spt, stages, smem = plan
+    threads, spt, stages, smem, lanes = plan
     # every CTA allocates all 512 tensor-memory columns of its SM: never let two of them share an SM (the second
     # would wait in tcgen05.alloc until the first, persistent, CTA exits)
     smem = max(smem, 117 * 1024)
@@ -253,6 +261,7 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     out.append(f'#define KX_TB {tb}')
     out.append(f'#define KX_NP {NP}')
     out.append(f'#define KX_P {spt}')
+    out.append(f'#define KX_L {lanes}')
     out.append(f'#define KX_NS {ns}')
     out.append(f'#define KX_BK2_BLOCK {threads}')
     out.append(f'#define KX_STAGES {stages}')
@@ -262,6 +271,9 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     # further measured no faster: GRI-3.0 633 / 629 / 589 M states/s for 1 / 3 / 9), more for one-state threads whose
     # column is half the work (EtOHKonnov 5: 96.6 vs 91.5 M, heptaneLu88 8: 244 vs 232 M)
     cu = opt.get('bk2_col_unroll') or (1 if spt == 2 else max(d for d in range(1, 9) if tb % d == 0))
+    if lanes > 1:
+        cu = tb // lanes                               # each half takes its half of a tile in one go
+    assert tb % cu == 0, 'bk2_col_unroll must divide the tile edge'
     out.append(f'#define KX_COL_UNROLL {cu}')
     out.append(f'#define KX_WR {wr}')
     out.append(f'#define KX_VROWS {vrows}')
@@ -273,7 +285,7 @@ def _emit_bk2_tmem(out, mech, fits, opt, tq):
     out.append(_table('kx_chunk_off', offs, qualifier='__constant__', ctype='int'))
     out.append(_table('kx_bk2_stream', stream, qualifier='__device__ const __align__(16)'))
     out.append('#include "kx_bk2_tmem.cuh"')
-    return smem, threads * spt, True
+    return smem, threads // lanes * spt, True
 
 
 def wilke_low_rank(M, tol=1e-13):
@@ -540,20 +552,20 @@ static int launch_bk2(long long n, long long offsetT, long long offset, double p
   static int n_sm[KXM_MAX_DEVICES] = {{}};
   const int dev = kxm_device();
   if (!configured[dev]) {{
-    if (int e = kxm_set_smem(kx_bk2<S, KX_P>, smem)) return e;
-    if (KX_P > 1) if (int e = kxm_set_smem(kx_bk2<S, 1>, smem)) return e;
+    if (int e = kxm_set_smem(kx_bk2<S, KX_P, KX_L>, smem)) return e;
+    if (KX_P > 1) if (int e = kxm_set_smem(kx_bk2<S, 1, KX_L>, smem)) return e;
     if (cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1002;
     configured[dev] = true;
   }}
-  const bool small = KX_P > 1 && n <= (long long)n_sm[dev] * block * (KX_P - 1);
-  const int per_cta = block * (small ? 1 : KX_P);
+  const bool small = KX_P > 1 && n <= (long long)n_sm[dev] * (block / KX_L) * (KX_P - 1);
+  const int per_cta = (block / KX_L) * (small ? 1 : KX_P);
   unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
   if (grid > (unsigned)n_sm[dev]) grid = (unsigned)n_sm[dev];
   if (small)
-    kx_bk2<S, 1><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
+    kx_bk2<S, 1, KX_L><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
                                                (S*)viscosity, (S*)rhoD, Tref);
   else
-    kx_bk2<S, KX_P><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
+    kx_bk2<S, KX_P, KX_L><<<grid, block, smem, stream>>>(n, offsetT, offset, (real)pressure, (const S*)state, (S*)conductivity,
                                                   (S*)viscosity, (S*)rhoD, Tref);
   return (int)cudaGetLastError();
 }}

@@ -184,33 +184,45 @@ KX_DEVICE void kx_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: 
 KX_DEVICE void kx_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ST: storage type of the state / result buffers (reference: dfloat); P: states per thread -- KX_P for full batches,
-// 1 for small launches (fewer than one KX_P-state batch per SM: half-size batches put twice as many SMs to work)
-template <typename ST, int P>
+// 1 for small launches (fewer than one KX_P-state batch per SM: half-size batches put twice as many SMs to work).
+// L: warps per state group.  L = 2 (KX_L, mechanisms whose X_k leave room for only 128 states per SM, i.e. one
+// one-state warp per scheduler): the state group of warp w is shared with warp w + 4 -- same TMEM lane quadrant, same
+// lanes, hence the same tensor-memory columns and the same X_k in shared memory.  The two warps split every loop over
+// species (rows of the Wilke passes by parity, columns of a diffusion tile by halves) and add their partial sums
+// through spare tensor-memory columns around a CTA barrier: two warps per scheduler for the same on-chip footprint,
+// no coefficient is fetched twice.
+template <typename ST, int P, int L>
 __global__ void __launch_bounds__(KX_BK2_BLOCK, 1)
 kx_bk2(const long long n_states, const long long offsetT, const long long offset, const real pressure,
        const ST* __restrict__ state, ST* __restrict__ conductivity, ST* __restrict__ viscosity,
        ST* __restrict__ rhoD, const double Tref)
 {
   extern __shared__ __align__(16) unsigned char kx_sm_raw[];
-  // PERSISTENT CTA of TT threads; a thread carries P states of the current batch (slots tt, tt + TT, ...):
-  // LDT = TT * P states per batch.
-  constexpr int TT = KX_BK2_BLOCK, LDT = TT * P, TB = KX_TB, NB = KX_NB;
-  constexpr int NWT = TT / 32, STG = KX_STAGES, R = KX_WR, RU = KX_WR + 6, RV = KX_WR + 12;
+  // PERSISTENT CTA of TT threads = L halves of TS threads; a thread carries P states of the current batch (slots
+  // ts, ts + TS, ...): LDT = TS * P states per batch.
+  constexpr int TT = KX_BK2_BLOCK, TS = TT / L, LDT = TS * P, TB = KX_TB, NB = KX_NB;
+  constexpr int NWT = TT / 32, NWS = NWT / L, STG = KX_STAGES, R = KX_WR, RU = KX_WR + 6, RV = KX_WR + 12;
   constexpr int N_CHUNKS = KX_N_CHUNKS;
   constexpr int C_U = KX_NVC, C_D = C_U + KX_NUC;   // first chunk of U, of the tiles
-  constexpr int TM_SLOTS = (NWT + 3) / 4;                               // warps per TMEM lane quadrant
-  constexpr int TM_STATE = 2 * (KX_NS + 2);                             // columns per state: S_k, then Mbar and sqrt(T)/R
+  constexpr int G = L == 1 ? KX_COL_UNROLL : TB / L;                    // columns per group of the pair loop
+  constexpr int NX = L == 1 ? 0 : (3 * R + 2 > TB ? 3 * R + 2 : TB);    // doubles a half hands to the other at a time
+  constexpr int TM_SLOTS = (NWS + 3) / 4;                               // state groups per TMEM lane quadrant
+  // columns per state: S_k, Mbar and sqrt(T), then one exchange area per half
+  constexpr int TM_STATE = 2 * (KX_NS + 2 + L * NX);
   constexpr int TM_COLS = TM_SLOTS * P * TM_STATE;                      // columns in use per TMEM lane
   static_assert((STG & (STG - 1)) == 0 && TT % 32 == 0 && TM_COLS <= 512 && KX_NS >= KX_NP - KX_TB, "shape");
+  static_assert(L == 1 || (L == 2 && NWS % 4 == 0 && TB % 2 == 0), "two warps per state group: 128-thread halves, even tile edge");
+  static_assert(TB % G == 0, "the column group must divide the tile edge");
   static_assert(C_D + KX_N_DTILES == N_CHUNKS, "chunk table");
   static_assert(sizeof(ST) == 8, "the tensor-memory BK2 kernel serves FP64 buffers");
   const int tt = threadIdx.x, warp = threadIdx.x >> 5;
+  const int ts = L == 1 ? tt : tt % TS, half = L == 1 ? 0 : tt / TS;
   uint64_t* const full = reinterpret_cast<uint64_t*>(kx_sm_raw);          // STG full + STG empty barriers
   uint64_t* const empty = full + STG;
   unsigned* const tm_base_slot = reinterpret_cast<unsigned*>(empty + STG);
   real* const buf0 = reinterpret_cast<real*>(kx_sm_raw + 16 * STG + 16);  // STG stages of KX_CHUNK_MAX reals
-  // X[k] of state p at X[k * LDT + p * TT]; only the KX_N real species have a row
-  real* __restrict__ X = buf0 + STG * KX_CHUNK_MAX + tt;
+  // X[k] of state p at X[k * LDT + p * TS]; only the KX_N real species have a row
+  real* __restrict__ X = buf0 + STG * KX_CHUNK_MAX + ts;
   const unsigned x_smem = kx_smem_addr(X);
   auto x_row = [&](int k) { return (k < KX_N ? k : KX_N - 1) * LDT; };
 
@@ -239,10 +251,36 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();   // mbarrier inits + TMEM base address visible
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // this thread's S_k of state p: lane quadrant (warp % 4), column TM_STATE ((warp / 4) P + p) + 2 k
+  // this thread's S_k of state p: lane quadrant (warp % 4), column TM_STATE (group slot x P + p) + 2 k
   const unsigned tm0 = *reinterpret_cast<volatile unsigned*>(tm_base_slot) + ((unsigned)(warp & 3) << 21) +
-                       (unsigned)((warp >> 2) * P * TM_STATE);
+                       (unsigned)(((warp % NWS) >> 2) * P * TM_STATE);
 #define KX_TM(p, k) (tm0 + (unsigned)((p) * TM_STATE + 2 * (k)))
+  // the halves of a state group meet here: tensor-memory stores of one visible to the loads of the other
+  auto meet = [&]() {
+    if constexpr (L > 1) {
+      kx_tm_wait_st();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+  };
+  // v[0..N) += the other half's v: through the exchange areas behind the sums (two barriers: publish, then release)
+  auto add_other_half = [&](auto& v, int p) {
+    if constexpr (L > 1) {
+      constexpr int N = sizeof(v) / sizeof(real);
+      static_assert(N <= NX, "exchange area");
+      real (&vv)[N] = reinterpret_cast<real (&)[N]>(v);
+      kx_tm_store<N>(KX_TM(p, KX_NS + 2 + half * NX), vv);
+      meet();
+      unsigned raw[2 * N];
+      real o[N];
+      kx_tm_load<N>(KX_TM(p, KX_NS + 2 + (1 - half) * NX), raw);
+      kx_tm_wait_ld();
+      kx_tm_unpack<N>(raw, o);
+#pragma unroll
+      for (int i = 0; i < N; i++) vv[i] += o[i];
+    }
+  };
 
   if (tt == 0) {
 #pragma unroll
@@ -268,17 +306,17 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
   };
   // state index of slot p of a batch (tail slots recompute the last state and store nothing)
   auto state_id = [&](int batch, int p) -> long long {
-    const long long gid = (long long)batch * LDT + (p * TT + tt);
+    const long long gid = (long long)batch * LDT + (p * TS + ts);
     return gid < n_states ? gid : n_states - 1;
   };
-  // fetch the mass fractions of species [k0, k1) of `batch` into this thread's own X slots (raw Y_k; they are
-  // turned into Y_k / M_k when that batch starts).  Nobody else reads or writes those slots.
+  // fetch the mass fractions of species [k0, k1) of `batch` (this half: those of its parity) into the state's X
+  // slots (raw Y_k; the same half turns them into Y_k / M_k when that batch starts).
   auto prefetch_rows = [&](int batch, int k0, int k1) {
 #pragma unroll
     for (int p = 0; p < P; p++) {
       const ST* src = state + state_id(batch, p) + offsetT;
-      for (int k = k0; k < k1; k++)
-        kx_cp_async8_nc(x_smem + (unsigned)((k * LDT + p * TT) * sizeof(real)), src + (size_t)k * offset);
+      for (int k = k0 + ((k0 + half) & (L - 1)); k < k1; k += L)
+        kx_cp_async8_nc(x_smem + (unsigned)((k * LDT + p * TS) * sizeof(real)), src + (size_t)k * offset);
     }
     kx_cp_async_commit();
   };
@@ -292,7 +330,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
     const bool has_next = batch + b_step < n_batches;
     real lnT[P], lnT2[P], lnT4[P], Mbar[P];
     // (state indices are recomputed where they are needed instead of being held in registers across the pair loop)
-    auto is_live = [&](int p) { return (long long)batch * LDT + (p * TT + tt) < n_states; };
+    auto is_live = [&](int p) { return (long long)batch * LDT + (p * TS + ts) < n_states; };
 
     // ---- mole fractions (transportProps.okl:23-35): the rows were fetched into X while the previous batch was in
     //      its pair loop; one pass over shared memory turns Y_k into Y_k / M_k and sums ----
@@ -306,6 +344,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
       }
 #ifdef KX_BK2_NO_PREFETCH
       // development switch: the round-1 prologue (batches of 32 independent row loads straight from global memory)
+      static_assert(L == 1, "development switch");
       constexpr int LB = 32;
 #pragma unroll
       for (int k0 = 0; k0 < KX_N; k0 += LB) {
@@ -319,24 +358,26 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         for (int p = 0; p < P; p++)
 #pragma unroll
           for (int i = 0; i < LB; i++)
-            if (k0 + i < KX_N) X[(k0 + i) * LDT + p * TT] = (real)y[p][i];
+            if (k0 + i < KX_N) X[(k0 + i) * LDT + p * TS] = (real)y[p][i];
       }
 #else
       kx_cp_async_wait_all();
 #endif
 #pragma unroll 8
-      for (int k = 0; k < KX_N; k++) {
+      for (int k = half; k < KX_N; k += L) {
 #pragma unroll
         for (int p = 0; p < P; p++) {
-          const real yi = X[k * LDT + p * TT];
+          const real yi = X[k * LDT + p * TS];
           const real w = (yi > (real)0 ? yi : (real)0) * kx_rcpM[k];
-          X[k * LDT + p * TT] = w;
+          X[k * LDT + p * TS] = w;
           acc[p] += w;
         }
       }
 #pragma unroll
       for (int p = 0; p < P; p++) {
-        Mbar[p] = kx_rcp(acc[p]);
+        real a1[1] = {acc[p]};
+        add_other_half(a1, p);
+        Mbar[p] = kx_rcp(a1[0]);
         const double Td = Tref * (double)t_raw[p];
         lnT[p] = (real)kx_log(Td);
         lnT2[p] = lnT[p] * lnT[p];
@@ -344,10 +385,11 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         // Mbar (after the first Wilke pass) and sqrt(T) are only needed where results are stored: parked in this
         // thread's tensor-memory columns so that the loops have their registers (they run at the 255-register limit)
         const real park[2] = {Mbar[p], kx_sqrt((real)Td)};
-        kx_tm_store<2>(KX_TM(p, KX_NS), park);
+        if (half == 0) kx_tm_store<2>(KX_TM(p, KX_NS), park);
       }
+      meet();                       // the exchange areas are free again; the parked scalars are visible
     }
-    // sqrt(T) of state p, back from tensor memory
+    // Mbar and sqrt(T) of state p, back from tensor memory
     auto parked = [&](int p, real (&v)[2]) {
       unsigned praw[4];
       kx_tm_wait_st();
@@ -378,15 +420,15 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll 1
         for (int jb = c * (KX_VROWS / TB); jb < jb1; jb++, cv += TB * RV) {
 #pragma unroll 1      // one species row per iteration: ~3 KB of code, resident in the L0 instruction cache
-          for (int jj = 0; jj < TB; jj++) {
+          for (int jj = (jb * TB + half) & (L - 1); jj < TB; jj += L) {      // this half: the species of its parity
             const int j = jb * TB + jj;
             const real* row = cv + jj * RV;
             const real m4 = row[10];
             real x[P], xb[P], xbb[P];
 #pragma unroll
             for (int p = 0; p < P; p++) {
-              x[p] = j < KX_N ? X[x_row(j) + p * TT] * Mbar[p] : (real)0;
-              if (j < KX_N) X[x_row(j) + p * TT] = x[p];
+              x[p] = j < KX_N ? X[x_row(j) + p * TS] * Mbar[p] : (real)0;
+              if (j < KX_N) X[x_row(j) + p * TS] = x[p];
               const real lam = kx_quartic(row, lnT[p], lnT2[p], lnT4[p]);
               s1[p] = fma(x[p], lam, s1[p]);
               s2[p] = fma(x[p], kx_rcp(lam), s2[p]);
@@ -411,11 +453,29 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         }
         release();
       }
+      if constexpr (L > 1) {
+        // both halves need the complete projections for their share of the second pass
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+          real pack[3 * R + 2];
+#pragma unroll
+          for (int q = 0; q < R; q++) { pack[q] = t0[p][q]; pack[R + q] = t1[p][q]; pack[2 * R + q] = t2[p][q]; }
+          pack[3 * R] = s1[p];
+          pack[3 * R + 1] = s2[p];
+          add_other_half(pack, p);
+#pragma unroll
+          for (int q = 0; q < R; q++) { t0[p][q] = pack[q]; t1[p][q] = pack[R + q]; t2[p][q] = pack[2 * R + q]; }
+          s1[p] = pack[3 * R];
+          s2[p] = pack[3 * R + 1];
+        }
+        meet();
+      }
 #pragma unroll
       for (int p = 0; p < P; p++) {
         real pk[2];
         parked(p, pk);
-        if (is_live(p)) kx_st_stream(conductivity + state_id(batch, p), (ST)(pk[1] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
+        if (half == 0 && is_live(p))
+          kx_st_stream(conductivity + state_id(batch, p), (ST)(pk[1] * ((real)0.5 * (s1[p] + kx_rcp(s2[p])))));
       }
 #pragma unroll
       for (int p = 0; p < P; p++)
@@ -428,8 +488,10 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
       for (int c = 0; c < KX_NUC; c++) {
         const real* __restrict__ cu = acquire();
         const int k1 = min(KX_N, (c + 1) * KX_UROWS);
+        const int kf = c * KX_UROWS + ((c * KX_UROWS + half) & (L - 1));
+        cu += (kf - c * KX_UROWS) * RU;
 #pragma unroll 2
-        for (int k = c * KX_UROWS; k < k1; k++, cu += RU) {
+        for (int k = kf; k < k1; k += L, cu += L * RU) {
           const real m4 = cu[R + 5];
           real v[P], w[P], w2[P], ph[P][4];
 #pragma unroll
@@ -451,17 +513,20 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll
           for (int p = 0; p < P; p++) {
             const real phi = (ph[p][0] + ph[p][1]) + (ph[p][2] + ph[p][3]);
-            vis[p] = fma(X[k * LDT + p * TT] * (v[p] * v[p]), kx_rcp(phi), vis[p]);
+            vis[p] = fma(X[k * LDT + p * TS] * (v[p] * v[p]), kx_rcp(phi), vis[p]);
           }
         }
         release();
       }
 #pragma unroll
       for (int p = 0; p < P; p++) {
+        real v1[1] = {vis[p]};
+        add_other_half(v1, p);
         real pk[2];
         parked(p, pk);
-        if (is_live(p)) kx_st_stream(viscosity + state_id(batch, p), (ST)(pk[1] * vis[p]));
+        if (half == 0 && is_live(p)) kx_st_stream(viscosity + state_id(batch, p), (ST)(pk[1] * v1[0]));
       }
+      meet();       // every X_j is final (written by the half of its parity) before anybody's pair loop reads it
     }
 
     // ---- mixture-averaged diffusion: S_k = sum_{j != k} X_j / D_kj over tiles of the lower triangle, row blocks
@@ -469,24 +534,26 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
     //      block kb ends its S_k are complete (the blocks above have already added their column contributions in
     //      tensor memory): rho * D_km of the block is formed and stored at once (mix_transport.py:621-622 and
     //      transportProps.okl:43-47; p and Mbar cancel), and the block's X rows are refilled with the next batch ----
-    if (has_next) {
+    if (has_next && half == 0) {
 #pragma unroll
       for (int p = 0; p < P; p++) asm volatile("prefetch.global.L2 [%0];" ::"l"(state + state_id(batch + b_step, p)));
     }
-    {   // the column sums of blocks 0 .. NB-2 start from zero
+    if (half == 0) {   // the column sums of blocks 0 .. NB-2 start from zero
       const real zero[TB] = {};
 #pragma unroll 1
       for (int jb = 0; jb < NB - 1; jb++)
 #pragma unroll
         for (int p = 0; p < P; p++) kx_tm_store<TB>(KX_TM(p, jb * TB), zero);
     }
+    meet();
 #pragma unroll 1
     for (int kb = NB - 1; kb >= 0; kb--) {
       const bool top = kb == NB - 1;          // the top block never goes to tensor memory: its sums start here
       real xk[P][TB], sk[P][TB];
       {
         unsigned raw[P][2 * TB];
-        if (!top) {
+        const bool from_tm = !top && half == 0;      // the column contributions collected so far (one half adds them)
+        if (from_tm) {
           kx_tm_wait_st();
 #pragma unroll
           for (int p = 0; p < P; p++) kx_tm_load<TB>(KX_TM(p, kb * TB), raw[p]);
@@ -496,9 +563,9 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll
           for (int i = 0; i < TB; i++) {
             const int k = kb * TB + i;
-            xk[p][i] = k < KX_N ? X[x_row(k) + p * TT] : (real)0;
+            xk[p][i] = k < KX_N ? X[x_row(k) + p * TS] : (real)0;
           }
-        if (!top) {
+        if (from_tm) {
           kx_tm_wait_ld();
 #pragma unroll
           for (int p = 0; p < P; p++) kx_tm_unpack<TB>(raw[p], sk[p]);
@@ -511,72 +578,80 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
       }
 #pragma unroll 1
       for (int jb = 0; jb < kb; jb++) {
-        // One COLUMN j of the tile per iteration of a ROLLED loop: the column's mole fraction and running sum are
-        // scalars per state (shared / tensor memory, the sum fetched one column ahead), only the row block's xk / sk
-        // stay in registers.  The loop body is 9 pairs x P states = ~3 KB of code: it lives in the 6 KB L0
-        // instruction cache.  (Unrolled over the whole 9 x 9 tile the body is ~30 KB -- at the edge of the 32 KB
-        // L1.5 instruction cache: the round-1 body just fitted (hit rate 95 %), a few more instructions per pair
-        // and it thrashes: hit rate 77 %, no_instruction stalls x6, 434 instead of 644 M states/s.)
-        unsigned cur[P][2], nxt[P][2];
+        // G columns of the tile per iteration of a ROLLED loop (L = 1: KX_COL_UNROLL columns; L = 2: each half takes
+        // its half of the tile in one go).  A column's mole fraction and running sum are scalars per state (shared /
+        // tensor memory; the sums of a group travel together, fetched one group ahead), only the row block's xk / sk
+        // stay in registers.  One column = TB pairs x P states = ~3 KB of code, resident in the 6 KB L0 instruction
+        // cache.  (Unrolled over the whole 9 x 9 tile the body is ~30 KB -- at the edge of the 32 KB L1.5 instruction
+        // cache: the round-1 body just fitted (hit rate 95 %), a few more instructions per pair and it thrashes: hit
+        // rate 77 %, no_instruction stalls x6, 434 instead of 644 M states/s.)
+        unsigned cur[P][2 * G], nxt[P][2 * G];
         kx_tm_wait_st();
 #pragma unroll
-        for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB), cur[p]);
+        for (int p = 0; p < P; p++) kx_tm_load<G>(KX_TM(p, jb * TB + half * G), cur[p]);
         const real* __restrict__ tile = acquire();
-        constexpr int COL_UNROLL = KX_COL_UNROLL;
-#pragma unroll COL_UNROLL
-        for (int j = 0; j < TB; j++) {
-          real xj[P], sj[P];
-#pragma unroll
-          for (int p = 0; p < P; p++) xj[p] = X[(jb * TB + j) * LDT + p * TT];   // jb < kb: real species
+#pragma unroll 1
+        for (int j0 = half * G; j0 < TB; j0 += L * G) {
+          real sj[P][G];
           kx_tm_wait_ld();
 #pragma unroll
-          for (int p = 0; p < P; p++) {
-            asm volatile("" : "+r"(cur[p][0]), "+r"(cur[p][1]));
-            sj[p] = __hiloint2double((int)cur[p][1], (int)cur[p][0]);
+          for (int p = 0; p < P; p++) kx_tm_unpack<G>(cur[p], sj[p]);
+          if constexpr (L == 1) {
+            // the next group's sums (the last iteration fetches its own group again: harmless, unused)
+#pragma unroll
+            for (int p = 0; p < P; p++) kx_tm_load<G>(KX_TM(p, jb * TB + min(j0 + G, TB - G)), nxt[p]);
           }
-          // the next column's sum (the last iteration fetches one column past the tile: harmless, unused)
 #pragma unroll
-          for (int p = 0; p < P; p++) kx_tm_ld2(KX_TM(p, jb * TB + min(j + 1, TB - 1)), nxt[p]);
-          real d[P][TB];
-          const real* __restrict__ col = tile + j * KX_COL;
+          for (int jj = 0; jj < G; jj++) {
+            const int j = j0 + jj;
+            real xj[P];
 #pragma unroll
-          for (int i = 0; i + 1 < TB; i += 2) {      // two rows per record: five 16-byte loads
-            const real2* cp = reinterpret_cast<const real2*>(col + (i / 2) * 10);
-            const real2 c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
+            for (int p = 0; p < P; p++) xj[p] = X[(jb * TB + j) * LDT + p * TS];   // jb < kb: real species
+            real d[P][TB];
+            const real* __restrict__ col = tile + j * KX_COL;
+#pragma unroll
+            for (int i = 0; i + 1 < TB; i += 2) {      // two rows per record: five 16-byte loads
+              const real2* cp = reinterpret_cast<const real2*>(col + (i / 2) * 10);
+              const real2 c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3], c4 = cp[4];
+#pragma unroll
+              for (int p = 0; p < P; p++) {
+                const real qa = fma(c4.x, lnT4[p], fma(fma(c3.x, lnT[p], c2.x), lnT2[p], fma(c1.x, lnT[p], c0.x)));
+                const real qb = fma(c4.y, lnT4[p], fma(fma(c3.y, lnT[p], c2.y), lnT2[p], fma(c1.y, lnT[p], c0.y)));
+                d[p][i] = KX_RCP_DIFF ? qa : KX_PAIR_RCP(qa);
+                d[p][i + 1] = KX_RCP_DIFF ? qb : KX_PAIR_RCP(qb);
+              }
+            }
+            if (TB & 1) {
+              const real* cp = col + (TB / 2) * 10;
+              const real2 c01 = *reinterpret_cast<const real2*>(cp), c23 = *reinterpret_cast<const real2*>(cp + 2);
+              const real c4 = cp[4];
+#pragma unroll
+              for (int p = 0; p < P; p++) {
+                const real q = fma(c4, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
+                d[p][TB - 1] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
+              }
+            }
 #pragma unroll
             for (int p = 0; p < P; p++) {
-              const real qa = fma(c4.x, lnT4[p], fma(fma(c3.x, lnT[p], c2.x), lnT2[p], fma(c1.x, lnT[p], c0.x)));
-              const real qb = fma(c4.y, lnT4[p], fma(fma(c3.y, lnT[p], c2.y), lnT2[p], fma(c1.y, lnT[p], c0.y)));
-              d[p][i] = KX_RCP_DIFF ? qa : KX_PAIR_RCP(qa);
-              d[p][i + 1] = KX_RCP_DIFF ? qb : KX_PAIR_RCP(qb);
-            }
-          }
-          if (TB & 1) {
-            const real* cp = col + (TB / 2) * 10;
-            const real2 c01 = *reinterpret_cast<const real2*>(cp), c23 = *reinterpret_cast<const real2*>(cp + 2);
-            const real c4 = cp[4];
+              real se = 0, so = 0;
 #pragma unroll
-            for (int p = 0; p < P; p++) {
-              const real q = fma(c4, lnT4[p], fma(fma(c23.y, lnT[p], c23.x), lnT2[p], fma(c01.y, lnT[p], c01.x)));
-              d[p][TB - 1] = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
+              for (int i = 0; i < TB; i++) {
+                if (i & 1) so = fma(xk[p][i], d[p][i], so); else se = fma(xk[p][i], d[p][i], se);
+                sk[p][i] = fma(xj[p], d[p][i], sk[p][i]);
+              }
+              sj[p][jj] += se + so;
             }
           }
 #pragma unroll
           for (int p = 0; p < P; p++) {
-            real se = 0, so = 0;
+            kx_tm_store<G>(KX_TM(p, jb * TB + j0), sj[p]);
+            if constexpr (L == 1) {
 #pragma unroll
-            for (int i = 0; i < TB; i++) {
-              if (i & 1) so = fma(xk[p][i], d[p][i], so); else se = fma(xk[p][i], d[p][i], se);
-              sk[p][i] = fma(xj[p], d[p][i], sk[p][i]);
+              for (int q = 0; q < 2 * G; q++) cur[p][q] = nxt[p][q];
             }
-            sj[p] += se + so;
-            unsigned w2[2] = {(unsigned)__double2loint(sj[p]), (unsigned)__double2hiint(sj[p])};
-            kx_tm_st2(KX_TM(p, jb * TB + j), w2);
-            cur[p][0] = nxt[p][0];
-            cur[p][1] = nxt[p][1];
           }
         }
-        kx_tm_wait_ld();       // the look-ahead load of the last column
+        if constexpr (L == 1) kx_tm_wait_ld();       // the look-ahead load of the last group
         release();
       }
       // diagonal tile: pairs i > j inside the block
@@ -586,10 +661,10 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         for (int i = 1; i < TB; i++) {
 #pragma unroll
           for (int j = 0; j < i; j++) {
+            if (L > 1 && ((i + j) & (L - 1)) != half) continue;      // the halves take alternate pairs
             // coefficient m of pair (i, j): paired rows interleaved, the odd last row on its own (see KX_COL)
             const real* cp = tile + j * KX_COL + (i / 2) * 10 + ((i | 1) < TB ? (i & 1) : 0);
-            constexpr int CS = 2;
-            const int cs = (i | 1) < TB ? CS : 1;
+            const int cs = (i | 1) < TB ? 2 : 1;
             const real c0 = cp[0], c1 = cp[cs], c2 = cp[2 * cs], c3 = cp[3 * cs], c4 = cp[4 * cs];
 #pragma unroll
             for (int p = 0; p < P; p++) {
@@ -602,7 +677,12 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         }
         release();
       }
-      // S_k of this block are final: rho * D_km = sqrt(T) / R * (Mbar - M_k X_k) / S_k, stored while the pipe goes on
+      // S_k of this block are final (L = 2: after the halves have added their partial sums):
+      // rho * D_km = sqrt(T) / R * (Mbar - M_k X_k) / S_k, stored while the pipe goes on
+      if constexpr (L > 1) {
+#pragma unroll
+        for (int p = 0; p < P; p++) add_other_half(sk[p], p);
+      }
       unsigned praw[P][4];
       kx_tm_wait_st();
 #pragma unroll
@@ -617,6 +697,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         ST* const dst = rhoD + state_id(batch, p) + (size_t)(kb * TB) * offset;
 #pragma unroll
         for (int i = 0; i < TB; i++) {
+          if (L > 1 && (i / (TB / L)) != half) continue;       // each half stores the rows of its half of the block
           const int k = kb * TB + i;
           if (k < KX_N) {
             const real num = fma(-kx_M[k], xk[p][i], Mb);
@@ -625,6 +706,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
           }
         }
       }
+      meet();       // both halves are done with the block's X rows and with the exchange areas
       // the block's X rows are dead: the next batch's mass fractions move in
 #ifndef KX_BK2_NO_PREFETCH
       if (has_next) prefetch_rows(batch + b_step, kb * TB, min(KX_N, kb * TB + TB));

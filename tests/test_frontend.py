@@ -159,7 +159,7 @@ def test_bk2_kernel_plan():
     # tensor memory: ceil(warps / 4) x P states per lane, each KX_NS sums + 2 parked scalars; the top row block never
     # goes to tensor memory (descending block order), so KX_NS = KX_NP - KX_TB
     assert d['KX_NS'] == d['KX_NP'] - d['KX_TB']
-    assert -(-(d['KX_BK2_BLOCK'] // 32) // 4) * d['KX_P'] * 2 * (d['KX_NS'] + 2) <= 512
+    assert d['KX_L'] == 1 and -(-(d['KX_BK2_BLOCK'] // 32) // 4) * d['KX_P'] * 2 * (d['KX_NS'] + 2) <= 512
     offs = [int(x) for x in re.search(r'kx_chunk_off\[(\d+)\] = \{([^}]*)\}', src).group(2).split(',')]
     assert len(offs) == d['KX_N_CHUNKS'] + 1 and offs[0] == 0
     sizes = np.diff(offs)
@@ -170,12 +170,20 @@ def test_bk2_kernel_plan():
     assert smem <= 227 * 1024
     assert smem >= (d['KX_STAGES'] * d['KX_CHUNK_MAX'] + 53 * 512) * 8
     # small launches run the one-state-per-thread instantiation of the same kernel
-    assert 'kx_bk2<S, 1><<<' in src and 'kx_bk2<S, KX_P><<<' in src
-    # the 129-species mechanism: 192 one-state threads (6 warps: lane quadrants 0 and 1 carry two warps)
+    assert 'kx_bk2<S, 1, KX_L><<<' in src and 'kx_bk2<S, KX_P, KX_L><<<' in src
+    # the 129-species mechanism: X_k leaves room for 128 states per SM; 256 threads work as two halves sharing them
+    # (KX_L = 2), each half takes half of a tile's columns, and the exchange areas fit the 512 tensor-memory columns
     m = mech('EtOHKonnov')
     d = _macros(emit_module(m, fit_transport(m))[0])
-    assert d['KX_P'] == 1 and d['KX_BK2_BLOCK'] == 192 and 2 * 2 * (d['KX_NS'] + 2) <= 512
-    assert (129 * 192 + d['KX_STAGES'] * d['KX_CHUNK_MAX']) * 8 <= 227 * 1024
+    assert d['KX_P'] == 1 and d['KX_L'] == 2 and d['KX_BK2_BLOCK'] == 256 and d['KX_TB'] % 2 == 0
+    assert d['KX_COL_UNROLL'] == d['KX_TB'] // 2
+    nx = max(3 * d['KX_WR'] + 2, d['KX_TB'])
+    assert 2 * (d['KX_NS'] + 2 + 2 * nx) <= 512
+    assert (129 * 128 + d['KX_STAGES'] * d['KX_CHUNK_MAX']) * 8 <= 227 * 1024
+    # a mechanism that holds 256 one-state threads keeps one warp per state group
+    m = mech('heptaneLu88')
+    d = _macros(emit_module(m, fit_transport(m))[0])
+    assert d['KX_P'] == 1 and d['KX_L'] == 1 and d['KX_BK2_BLOCK'] == 256
     # small mechanisms keep the one-state-per-thread kernel with the dense Wilke matrix
     m = mech('LiDryer')
     src, _ = emit_module(m, fit_transport(m))

@@ -122,11 +122,14 @@ def test_largest_mechanism_etoh(kinetix):
     e_all, e_sig = elementwise_errors(new, ref)
     print(f'{mech} BK1 vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}; element-wise all {e_all:.3e} significant {e_sig:.3e}')
     assert rate_err <= TOL and hrr_err <= TOL and e_sig <= TOL
-    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
-    rc, rv, rrd = orc.transport(st, 1.0)
+    # BK2: the 129-species kernel runs 256 threads as two halves sharing 128 states (warps w and w + 4 own the same
+    # tensor-memory lanes and split every loop over species); 2.4 batches per persistent CTA plus a ragged tail
+    st2 = synthetic_states(N, 148 * 128 * 2 + 57 * 128 + 77, seed=9)
+    cond, visc, rhoD = _run_bk2(kinetix, st2, 1.0)
+    rc, rv, rrd = orc.transport(st2, 1.0)
     errs = rel_err(cond, rc), rel_err(visc, rv), rel_err(rhoD, rrd)
-    print(f'{mech} BK2 vs {orc.kind}: {errs}')
-    assert max(errs) <= TOL
+    print(f'{mech} BK2 {st2.shape[1]} states vs {orc.kind}: {errs}')
+    assert np.isfinite(rhoD).all() and max(errs) <= TOL
 
 
 @pytest.mark.parametrize('mech', ['gri30', 'LiDryer'])
