@@ -309,7 +309,8 @@ class BK1Emitter:
     # ---- main --------------------------------------------------------------------------------
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
              reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False,
-             tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0, routine=False, kbase_ahead=0):
+             tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0, routine=False, kbase_ahead=0,
+             cold_conc_only=False, gibbs_prefer_tm=False):
         """block / min_blocks: launch bounds.
         routine: emit the reference-signature DEVICE FUNCTION `kinetix_species_rates(lnT, T, T2, T3, T4, rcpT, P, lnP,
           Ci, wdot)` (reference reaction_rates.py:560-562) instead of the kernel: concentrations come from `Ci[]`,
@@ -320,6 +321,9 @@ class BK1Emitter:
           while they are live, as long as the thread's slots in use stay below `cold_slot_cap`: explicit placement of
           the values ptxas would otherwise spill to local memory (heptaneLu88: 88 species, 29 slots, 2.7 KB of spill
           loads at 168 registers while two thirds of its shared-memory budget are idle).
+        cold_conc_only: the cold placement moves only the (read-only) concentration C_k to a slot; the accumulator
+          wdot_k, the read-modify-write half, stays in a register.  gibbs_prefer_tm: exp(+-g_k) take tensor-memory
+          slots first, leaving the shared-memory slots to the concentrations.
         tmem_slots: > 0: that many doubles per thread of TENSOR MEMORY hold scratch slots beside at most `smem_cap`
           shared-memory slots (large mechanisms: EtOHKonnov needs 210 slots = 1.7 KB per thread, which limits a
           shared-memory-only kernel to 4 warps per SM).  Third-body sums go to tensor memory first, exp(+-g_k) to
@@ -588,7 +592,10 @@ class BK1Emitter:
         # slots, lost its third CTA per SM and ran at 676 instead of 962 M states/s).  A species' exp(+-g) slots are
         # busy from its activation to its retirement; a cold segment adds two more over the same span.
         cold_plan = set()
-        if cold_uses and gibbs_in_smem and not tmem_slots:
+        n_cold = 1 if cold_conc_only else 2
+        if tmem_slots and cold_conc_only:
+            cold_slot_cap = smem_cap + tmem_slots - 2
+        if cold_uses and gibbs_in_smem and (not tmem_slots or cold_conc_only):
             n_pos = len(order)
             usage = [len(eff_slot) + len([n for n in need_ln if eff_smem])] * (n_pos + 1)
             for k, segs in segments.items():
@@ -599,21 +606,27 @@ class BK1Emitter:
                 if len(uses[k]) > cold_uses:
                     continue
                 for si, (a, b) in enumerate(segments[k]):
-                    if max(usage[a:b + 1]) + 2 <= cold_slot_cap:
+                    if max(usage[a:b + 1]) + n_cold <= cold_slot_cap:
                         cold_plan.add((k, si))
                         for pos in range(a, b + 1):
-                            usage[pos] += 2
+                            usage[pos] += n_cold
 
         def place(k, segment=0):
             """decide where species k lives for this live segment"""
             if not (cold_uses and gibbs_in_smem) or len(uses[k]) > cold_uses:
                 return
-            if tmem_slots:
+            if tmem_slots and not cold_conc_only:
                 # tensor-memory layout: shared-memory slots are capped by smem_cap, in-use check with head-room for the
                 # exp(+-g) of the next activations (the overflow goes to tensor memory, not to a bigger CTA)
                 if (n_slots - len(free_slots)) + 2 + 6 > smem_cap:
                     return
             elif (k, segment) not in cold_plan:
+                return
+            if cold_conc_only:
+                a = take_slot(smem_only=True)
+                if a is not None:
+                    mem_cs[k] = a
+                    self.cold_activations += 1
                 return
             a, b = take_slot(smem_only=True), take_slot(smem_only=True)
             if a is None or b is None:
@@ -686,9 +699,9 @@ class BK1Emitter:
                 gmin, gmax = min(gmin, g), max(gmax, g)
             glo, ghi = min(gmin * 1.05, gmin * 0.95) - 5, max(gmax * 1.05, gmax * 0.95) + 5
             if need_pos[k]:
-                self.eg_slot[k] = take_slot() if gibbs_in_smem else None
+                self.eg_slot[k] = take_slot(prefer_tm=gibbs_prefer_tm) if gibbs_in_smem else None
             if need_neg[k]:
-                self.rg_slot[k] = take_slot() if gibbs_in_smem else None
+                self.rg_slot[k] = take_slot(prefer_tm=gibbs_prefer_tm) if gibbs_in_smem else None
             w('{')
             w(f'  const double g = fma(fma(fma(fma({c[5]}, T, {c[4]}), T, {c[3]}), T, {c[2]}), T, '
               f'fma({c[1]}, lnT, fma({c[6]}, rcpT, {c[0]})));')

@@ -332,6 +332,7 @@ def emit_module(mech, fits, options=None, single_precision=False):
                      opt['reorder'], opt['prefetch'], opt['ring'], opt['pin_loads'], opt['l1_keep'], opt['keep_until'], opt['live_cap'], opt['eff_in_smem'], opt['nasa_indexed'],
                      tmem_slots=bk1_tm['slots'], smem_cap=bk1_tm['smem_cap'], tmem_cols=bk1_tm.get('cols', 512),
                      cold_uses=opt.get('cold_uses', 0), cold_slot_cap=opt.get('cold_slot_cap', 0),
+                     cold_conc_only=opt.get('cold_conc_only', False), gibbs_prefer_tm=opt.get('gibbs_prefer_tm', False),
                      kbase_ahead=opt.get('kbase_ahead', 0))
         return e, src
 
@@ -349,13 +350,15 @@ def emit_module(mech, fits, options=None, single_precision=False):
             bk1, bk1_src = emit_bk1()
     budget = 220 * 1024
     # mid-size mechanisms whose live set does not fit the registers but whose scratch slots leave most of the shared
-    # memory idle (heptaneLu88: 41 live species, 29 slots): rarely used species keep C_k / wdot_k in shared-memory slots
-    # while they are live -- explicit placement of what ptxas would spill (spill loads 2.7 KB -> 0.6 KB per state,
-    # 652 -> 682 M states/s; EtOHKonnov, whose slots are already full, loses 6 %: not applied in the tensor-memory layout)
+    # memory idle (heptaneLu88: 41 live species, 29 slots): the live species keep their (read-only) concentration C_k in
+    # a shared-memory slot, only the accumulators wdot_k stay in registers -- explicit placement of what ptxas would
+    # spill (spill loads 2.7 KB -> 0.66 KB per state).  M states/s: no placement 652, C_k and wdot_k of species with
+    # <= 40 uses in slots 676-682, C_k alone of those species 695, C_k of every species 712.  (GRI-3.0, 3 CTAs per SM
+    # kept: 942-947 vs 952; EtOHKonnov in the tensor-memory layout: 129-165 vs 162 -- not applied to either.)
     if (not sp and opt['gibbs_in_smem'] and 'cold_uses' not in (options or {})
             and bk1.schedule_stats.get('peak_live', 0) > 30 and bk1.smem_doubles_per_thread <= 40
             and bk1.smem_doubles_per_thread * 8 * 128 * 2 <= budget):
-        opt['cold_uses'], opt['cold_slot_cap'] = 40, 70
+        opt['cold_uses'], opt['cold_slot_cap'], opt['cold_conc_only'] = 1 << 20, 70, True
         bk1, bk1_src = emit_bk1()
     # large mechanisms: when the scratch slots (exp(+-g_k) of live species, third-body sums) allow at most one
     # 128-thread CTA per SM in shared memory (EtOHKonnov: 210 slots), spread them over shared AND tensor memory
