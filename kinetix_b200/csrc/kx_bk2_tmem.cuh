@@ -180,6 +180,11 @@ KX_DEVICE void kx_cp_async8_nc(unsigned smem_addr, const void* gptr)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
+// predicated shared-memory store (no branch in the instruction stream)
+KX_DEVICE void kx_sts_if(unsigned addr, double v, bool p)
+{
+  asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}" ::"r"(addr), "d"(v), "r"((unsigned)p) : "memory");
+}
 KX_DEVICE void kx_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 KX_DEVICE void kx_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -419,16 +424,26 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         const int jb1 = min(NB, (c + 1) * (KX_VROWS / TB));
 #pragma unroll 1
         for (int jb = c * (KX_VROWS / TB); jb < jb1; jb++, cv += TB * RV) {
-#pragma unroll 1      // one species row per iteration: ~3 KB of code, resident in the L0 instruction cache
-          for (int jj = (jb * TB + half) & (L - 1); jj < TB; jj += L) {      // this half: the species of its parity
+          // one species row per iteration of a ROLLED loop (~3 KB of code, resident in the L0 instruction cache),
+          // software-pipelined: the serial part of row j + L (two quartics, two Newton reciprocals: dependent chains
+          // with 5-8 cycle stalls between their instructions) is issued among the 6 R independent accumulations of
+          // row j.  KX_BK2_NO_SWP restores the unpipelined loop.
+          auto head = [&](int jj, real (&x)[P], real (&xb)[P], real (&xbb)[P]) {
             const int j = jb * TB + jj;
             const real* row = cv + jj * RV;
             const real m4 = row[10];
-            real x[P], xb[P], xbb[P];
 #pragma unroll
             for (int p = 0; p < P; p++) {
+#ifdef KX_BK2_NO_SWP
               x[p] = j < KX_N ? X[x_row(j) + p * TS] * Mbar[p] : (real)0;
               if (j < KX_N) X[x_row(j) + p * TS] = x[p];
+#else
+              // branch-free (a branch here would end the basic block and with it the interleaving): the load takes the
+              // clamped row, the store is predicated
+              const real xr = X[x_row(j) + p * TS];
+              x[p] = j < KX_N ? xr * Mbar[p] : (real)0;
+              kx_sts_if(x_smem + (unsigned)((x_row(j) + p * TS) * sizeof(real)), x[p], j < KX_N);
+#endif
               const real lam = kx_quartic(row, lnT[p], lnT2[p], lnT4[p]);
               s1[p] = fma(x[p], lam, s1[p]);
               s2[p] = fma(x[p], kx_rcp(lam), s2[p]);
@@ -436,6 +451,9 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
               xb[p] = x[p] * b;
               xbb[p] = xb[p] * b;
             }
+          };
+          auto project = [&](int jj, const real (&x)[P], const real (&xb)[P], const real (&xbb)[P]) {
+            const real* row = cv + jj * RV;
 #pragma unroll
             for (int q = 0; q < R; q += 2) {
               const real2 vv = *reinterpret_cast<const real2*>(row + 12 + q);
@@ -449,7 +467,28 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
                 t2[p][q + 1] = fma(vv.y, xbb[p], t2[p][q + 1]);
               }
             }
+          };
+          const int jj0 = (jb * TB + half) & (L - 1);          // this half: the species of its parity
+#ifdef KX_BK2_NO_SWP
+#pragma unroll 1
+          for (int jj = jj0; jj < TB; jj += L) {
+            real x[P], xb[P], xbb[P];
+            head(jj, x, xb, xbb);
+            project(jj, x, xb, xbb);
           }
+#else
+          real x[P], xb[P], xbb[P];
+          head(jj0, x, xb, xbb);
+#pragma unroll 1
+          for (int jj = jj0; jj + L < TB; jj += L) {
+            real xn[P], xbn[P], xbbn[P];
+            head(jj + L, xn, xbn, xbbn);
+            project(jj, x, xb, xbb);
+#pragma unroll
+            for (int p = 0; p < P; p++) { x[p] = xn[p]; xb[p] = xbn[p]; xbb[p] = xbbn[p]; }
+          }
+          project(jj0 + (TB - 1 - jj0) / L * L, x, xb, xbb);
+#endif
         }
         release();
       }
@@ -481,9 +520,9 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
       for (int p = 0; p < P; p++)
 #pragma unroll
         for (int q = 0; q < R; q++) t1[p][q] += t1[p][q];
-      real vis[P];
+      real vis[P], num_prev[P], phi_prev[P];       // (num_prev = 0, phi_prev = 1: the pipelined term of "no species")
 #pragma unroll
-      for (int p = 0; p < P; p++) vis[p] = 0;
+      for (int p = 0; p < P; p++) { vis[p] = 0; num_prev[p] = 0; phi_prev[p] = 1; }
 #pragma unroll 1
       for (int c = 0; c < KX_NUC; c++) {
         const real* __restrict__ cu = acquire();
@@ -493,6 +532,7 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll 2
         for (int k = kf; k < k1; k += L, cu += L * RU) {
           const real m4 = cu[R + 5];
+#ifdef KX_BK2_NO_SWP
           real v[P], w[P], w2[P], ph[P][4];
 #pragma unroll
           for (int p = 0; p < P; p++) {
@@ -515,11 +555,46 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
             const real phi = (ph[p][0] + ph[p][1]) + (ph[p][2] + ph[p][3]);
             vis[p] = fma(X[k * LDT + p * TS] * (v[p] * v[p]), kx_rcp(phi), vis[p]);
           }
+#else
+          // Phi_k = U_k.t_0 + w_k (U_k.2t_1) + w_k^2 (U_k.t_2): three dot products per state whose chains depend
+          // neither on each other nor on the quartic (the nested form fma(u, fma(w2, t2, fma(w, t1, t0)), ph) left ptxas
+          // 3-deep dependent triples that it issued 8 cycles apart: 671 stall cycles for 408 pipe cycles per two
+          // species); the previous species' Newton reciprocal is finished among this one's FMAs
+          real a0[P], a1[P], a2[P];
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            a0[p] = a1[p] = a2[p] = 0;
+            vis[p] = fma(num_prev[p], kx_rcp(phi_prev[p]), vis[p]);
+          }
+#pragma unroll
+          for (int q = 0; q < R; q += 2) {
+            const real2 uu = *reinterpret_cast<const real2*>(cu + q);
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+              a0[p] = fma(uu.x, t0[p][q], a0[p]);
+              a1[p] = fma(uu.x, t1[p][q], a1[p]);
+              a2[p] = fma(uu.x, t2[p][q], a2[p]);
+              a0[p] = fma(uu.y, t0[p][q + 1], a0[p]);
+              a1[p] = fma(uu.y, t1[p][q + 1], a1[p]);
+              a2[p] = fma(uu.y, t2[p][q + 1], a2[p]);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < P; p++) {
+            const real v = kx_quartic(cu + R, lnT[p], lnT2[p], lnT4[p]);
+            const real w = v * m4;
+            phi_prev[p] = fma(w, fma(w, a2[p], a1[p]), a0[p]);
+            num_prev[p] = X[k * LDT + p * TS] * (v * v);
+          }
+#endif
         }
         release();
       }
 #pragma unroll
       for (int p = 0; p < P; p++) {
+#ifndef KX_BK2_NO_SWP
+        vis[p] = fma(num_prev[p], kx_rcp(phi_prev[p]), vis[p]);
+#endif
         real v1[1] = {vis[p]};
         add_other_half(v1, p);
         real pk[2];
