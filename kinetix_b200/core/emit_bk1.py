@@ -164,7 +164,9 @@ class BK1Emitter:
         load with a register offset instead of two loads and a 64-bit select.  The offset differs between the
         lanes of a warp, so where the table lives matters (GRI-3.0, M states/s): 'ldg' = global memory through L1
         958 (default), 'smem' = per-CTA copy in shared memory 945, True / 'const' = __constant__ (the load
-        serialises over the two addresses and misses the 2 KB constant cache) 907; 128-bit LDG pairs 936."""
+        serialises over the two addresses and misses the 2 KB constant cache) 907; 128-bit LDG pairs 936; round 2:
+        an L1 evict-last hint on the table loads 916 (L1 hit rate 47 -> 41 %, more spills), no table at all -- both
+        ranges evaluated from constant operands, the result selected -- 790 (1.7 KB of spills)."""
         s = self.m.species[k]
         lo, hi = make(s.nasa_lo), make(s.nasa_hi)
         if getattr(self, 'nasa_indexed', False):
@@ -310,7 +312,7 @@ class BK1Emitter:
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
              reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False,
              tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0, routine=False, kbase_ahead=0,
-             cold_conc_only=False, gibbs_prefer_tm=False, probe_no_gibbs=False):
+             cold_conc_only=False, gibbs_prefer_tm=False):
         """block / min_blocks: launch bounds.
         routine: emit the reference-signature DEVICE FUNCTION `kinetix_species_rates(lnT, T, T2, T3, T4, rcpT, P, lnP,
           Ci, wdot)` (reference reaction_rates.py:560-562) instead of the kernel: concentrations come from `Ci[]`,
@@ -702,12 +704,6 @@ class BK1Emitter:
                 self.eg_slot[k] = take_slot(prefer_tm=gibbs_prefer_tm) if gibbs_in_smem else None
             if need_neg[k]:
                 self.rg_slot[k] = take_slot(prefer_tm=gibbs_prefer_tm) if gibbs_in_smem else None
-            if probe_no_gibbs:
-                # TIMING PROBE ONLY (wrong results): the slots get a placeholder, no NASA polynomial, no exp
-                for slots in (self.eg_slot, self.rg_slot):
-                    if k in slots:
-                        self.store(slots[k], 'rcpT')
-                return
             w('{')
             w(f'  const double g = fma(fma(fma(fma({c[5]}, T, {c[4]}), T, {c[3]}), T, {c[2]}), T, '
               f'fma({c[1]}, lnT, fma({c[6]}, rcpT, {c[0]})));')
