@@ -312,7 +312,8 @@ class BK1Emitter:
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
              reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False,
              tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0, routine=False, kbase_ahead=0,
-             cold_conc_only=False, gibbs_prefer_tm=False, sync_scope='cta'):
+             cold_conc_only=False, gibbs_prefer_tm=False, sync_scope='cta',
+             cold_volatile=False):
         """block / min_blocks: launch bounds.
         routine: emit the reference-signature DEVICE FUNCTION `kinetix_species_rates(lnT, T, T2, T3, T4, rcpT, P, lnP,
           Ci, wdot)` (reference reaction_rates.py:560-562) instead of the kernel: concentrations come from `Ci[]`,
@@ -589,7 +590,9 @@ class BK1Emitter:
         mem_cs, mem_wd, seg_of = {}, {}, {}
         self.cold_activations = 0
 
-        def CS(k):
+        def CS(k, write=False):
+            if k in mem_cs and cold_volatile and not write:
+                return f'kx_lds_here(gs + {mem_cs[k]} * {block})'
             return f'gs[{mem_cs[k]} * {block}]' if k in mem_cs else f'cs{k}'
 
         def WD(k):
@@ -673,9 +676,9 @@ class BK1Emitter:
             """species k becomes live: concentration, zeroed accumulator, exp(+-g_k/RT)"""
             place(k, seg_of.get(k, 0))
             if routine:
-                w(f'{CS(k)} = Ci[{k}]; {WD(k)} = 0.0;')
+                w(f'{CS(k, True)} = Ci[{k}]; {WD(k)} = 0.0;')
             elif k in self.kept and not reactivation:
-                w(f'{CS(k)} = w{k} * rho; {WD(k)} = 0.0;')
+                w(f'{CS(k, True)} = w{k} * rho; {WD(k)} = 0.0;')
             elif ring and not reactivation:
                 r = rank[k]
                 pending = max(0, min(ring - 1, len(act_order) - 1 - r))
@@ -687,15 +690,15 @@ class BK1Emitter:
             if routine or (k in self.kept and not reactivation):
                 pass
             elif reactivation:
-                w(f'{CS(k)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
+                w(f'{CS(k, True)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
             elif not ring and pin_loads:
                 # volatile max: keeps this activation ordered after the loads issued `prefetch` activations
                 # ahead (volatile asms are not reordered among themselves), so the compiler cannot sink those
                 # loads down to their first use
                 w(f'{{ double t; asm volatile("max.f64 %0, %1, 0d0000000000000000;" : "=d"(t) : "d"(y{k})); '
-                  f'{CS(k)} = t * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0; }}')
+                  f'{CS(k, True)} = t * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0; }}')
             else:
-                w(f'{CS(k)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
+                w(f'{CS(k, True)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
             if not (need_pos[k] or need_neg[k]):
                 return
             c, _, _ = self.nasa_select(k, gcoef)

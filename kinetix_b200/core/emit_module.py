@@ -332,16 +332,38 @@ def emit_module(mech, fits, options=None, single_precision=False):
                      opt['reorder'], opt['prefetch'], opt['ring'], opt['pin_loads'], opt['l1_keep'], opt['keep_until'], opt['live_cap'], opt['eff_in_smem'], opt['nasa_indexed'],
                      tmem_slots=bk1_tm['slots'], smem_cap=bk1_tm['smem_cap'], tmem_cols=bk1_tm.get('cols', 512),
                      cold_uses=opt.get('cold_uses', 0), cold_slot_cap=opt.get('cold_slot_cap', 0),
-                     cold_conc_only=opt.get('cold_conc_only', False), gibbs_prefer_tm=opt.get('gibbs_prefer_tm', False), sync_scope=opt.get('sync_scope', 'cta'),
+                     cold_conc_only=opt.get('cold_conc_only', False), gibbs_prefer_tm=opt.get('gibbs_prefer_tm', False), sync_scope=opt.get('sync_scope', 'cta'), cold_volatile=opt.get('cold_volatile', False),
                      kbase_ahead=opt.get('kbase_ahead', 0))
         return e, src
 
     bk1_tm = dict(slots=0, smem_cap=0)
     bk1, bk1_src = emit_bk1()
+    # FOUR warps per scheduler for mid-size mechanisms (round 2): two 256-thread CTAs per SM at 128 registers.  What makes
+    # 128 registers enough: the (read-only) concentrations C_k of the live species sit in shared-memory slots, the
+    # exp(+-g_k) and third-body sums go to TENSOR memory first (two CTAs x 256 columns = 64 doubles per thread) and
+    # overflow to shared memory (53 slots per thread), so the registers hold the accumulators wdot_k and temporaries
+    # only (GRI-3.0: 0.6 KB of spill loads, as at 168 registers before).  Two instruction streams per SM instead of
+    # three, four warps per scheduler instead of three to cover dependent-issue and instruction-fetch stalls.
+    # M states/s, classic layout (3-4 CTAs x 128 threads, 168 / 128 registers) -> this one:
+    #   gri30 956 -> 1020, gri30-35 1243 -> 1444, NH3Konnov_edit 880 -> 1289 (its 81 slots had allowed two 128-thread CTAs),
+    #   chempolimi_edit 1347 -> 1416, gri30-27 2538 -> 2656, gri30-20 3577 -> 3807, H2_new_mech 5324 -> 5826, H2_Konnov 5968 -> 6054;
+    #   not applied: LiDryer 13661 -> 12120 (8 live species), heptaneLu88 718 -> 709 (41 live species: 2.9 KB of spills).
+    # Around it on GRI-3.0: 4 x 128 threads 892 (four streams: no_instruction 1.86), 1 x 512 983, a CTA barrier every
+    # 12 / 16 / 24 / 32 reactions 994 / 1017 / 1007 / 993 and none 1022-1024, exp(+-g) of often-used species in shared
+    # memory instead 859-970 (more spills), wdot_k of rarely used species in slots too 900-995, C_k of rarely used species
+    # only 906, TMEM base address in a uniform register (563 R2UR fewer, 1.1 KB of spills) 1001.
+    layout_keys = ('block_bk1', 'minb_bk1', 'bk1_tmem', 'bk1_tmem_block', 'bk1_tmem_ctas', 'bk1_smem_cap', 'cold_uses',
+                   'sync_every', 'live_cap', 'gibbs_in_smem', 'ring', 'prefetch', 'eff_in_smem')
+    wide = (not sp and opt['gibbs_in_smem'] and not opt['ring'] and opt.get('bk1_layout', 'auto') != 'classic'
+            and not any(k in (options or {}) for k in layout_keys)
+            and 10 <= bk1.schedule_stats.get('peak_live', 0) <= 36 and bk1.smem_doubles_per_thread <= 53 + 64 - 2)
+    if wide:
+        opt.update(bk1_tmem=True, bk1_tmem_block=256, bk1_tmem_ctas=2, cold_uses=1 << 20, cold_conc_only=True,
+                   gibbs_prefer_tm=True, sync_every=0)
     # small mechanisms: few live species need few registers, more resident CTAs pay (M states/s, 8 Mi states;
     # FP64 3 -> 4 CTAs: LiDryer 13580 -> 13750, H2_Konnov 5470 -> 5980, gri30-20 3090 -> 3580; FP32 math 3 -> 6 / 8:
     # LiDryer 29100 -> 34100 / 35600 = 5.7 TB/s of HBM traffic, H2_Konnov 14660 -> 16880 / 16160, gri30-20 9200 -> 10170 / 9140)
-    if 'minb_bk1' not in (options or {}) and 'block_bk1' not in (options or {}):
+    if 'minb_bk1' not in (options or {}) and 'block_bk1' not in (options or {}) and not wide:
         peak = bk1.schedule_stats.get('peak_live', N)
         small = 4 if not sp else (8 if peak <= 8 else 6)
         # FP64, 17-25 live species: chempolimi_edit (21) 1180 -> 1340, gri30-27 (19) and gri30-35 (25) unchanged
@@ -355,7 +377,7 @@ def emit_module(mech, fits, options=None, single_precision=False):
     # spill (spill loads 2.7 KB -> 0.66 KB per state).  M states/s: no placement 652, C_k and wdot_k of species with
     # <= 40 uses in slots 676-682, C_k alone of those species 695, C_k of every species 712.  (GRI-3.0, 3 CTAs per SM
     # kept: 942-947 vs 952; EtOHKonnov in the tensor-memory layout: 129-165 vs 162 -- not applied to either.)
-    if (not sp and opt['gibbs_in_smem'] and 'cold_uses' not in (options or {})
+    if (not sp and opt['gibbs_in_smem'] and 'cold_uses' not in (options or {}) and not wide
             and bk1.schedule_stats.get('peak_live', 0) > 30 and bk1.smem_doubles_per_thread <= 40
             and bk1.smem_doubles_per_thread * 8 * 128 * 2 <= budget):
         opt['cold_uses'], opt['cold_slot_cap'], opt['cold_conc_only'] = 1 << 20, 70, True
@@ -377,7 +399,7 @@ def emit_module(mech, fits, options=None, single_precision=False):
             opt['block_bk1'], opt['minb_bk1'] = tm_block, tm_ctas
             # the 8 warps share one pass over ~0.75 MB of straight-line code: a barrier every 4 reactions keeps
             # them inside the same few KB of it (EtOHKonnov, M states/s: every 16: 118, 8: 135, 4: 157, 1: 148)
-            if 'sync_every' not in (options or {}):
+            if 'sync_every' not in (options or {}) and not wide:
                 opt['sync_every'] = 4
             # cap the live set (live-range splitting through the output rows, emit_bk1.py) so that the register
             # spills shrink (EtOHKonnov: 87 -> 60 live species, 10-13 KB -> 6 KB of spill loads per state for 57

@@ -84,14 +84,26 @@ def test_emitter_produces_a_module(name):
 
 
 def test_bk1_scratch_slot_plan():
-    """BK1 scratch slots (exp(+-g_k) of live species, third-body sums): small mechanisms keep them in shared memory
-    with several CTAs per SM; EtOHKonnov (210 slots) gets the shared + tensor memory layout -- one 256-thread CTA,
-    <= 110 shared-memory and <= 128 TMEM doubles per thread, live set capped -- and every TMEM value a reaction
-    reads is loaded (tcgen05.ld) inside that reaction's scope, behind a wait, before its first use."""
+    """BK1 scratch slots (exp(+-g_k) of live species, third-body sums, concentrations).  Mid-size mechanisms (10-36
+    live species: GRI-3.0 ...) run two 256-thread CTAs per SM at 128 registers -- four warps per scheduler -- with
+    the concentrations C_k of the live species in shared-memory slots and exp(+-g_k) / third-body sums in the CTA's 256
+    tensor-memory columns first; the smallest (LiDryer) keeps four 128-thread CTAs with everything in shared memory,
+    heptaneLu88 three with C_k in slots; EtOHKonnov (210 slots) gets one 256-thread CTA, <= 110 shared-memory and
+    <= 128 TMEM doubles per thread, live set capped.  Every TMEM value a reaction reads is loaded (tcgen05.ld) inside
+    that reaction's scope, behind a wait, before its first use."""
     import re
     src, stats = emit_module(mech('gri30'), None)
+    sch = stats['bk1_schedule']
+    assert '__launch_bounds__(256, 2)' in src and 'kx_tm_alloc_all<256>' in src and 'kx_tm_free_all<256>' in src
+    assert 0 < sch['tmem_slots'] <= 64 and sch['smem_slots'] <= 53 and sch['cold_activations'] == 53
+    assert sch['smem_slots'] * 8 * 256 * 2 <= 220 * 1024 and '__syncthreads();\n  // ---- unit' not in src
+    # the classic layout on request: three 128-thread CTAs at 168 registers, every slot in shared memory
+    src, stats = emit_module(mech('gri30'), None, options={'bk1_layout': 'classic'})
     assert 'kx_tm_alloc_all' not in src and '__launch_bounds__(128, 3)' in src
     assert stats['bk1_schedule']['tmem_slots'] == 0
+    for name, bounds in (('LiDryer', '(128, 4)'), ('heptaneLu88', '(128, 3)'), ('NH3Konnov_edit', '(256, 2)'),
+                         ('H2_Konnov', '(256, 2)')):
+        assert f'__launch_bounds__{bounds}' in emit_module(mech(name), None)[0], name
 
     src, stats = emit_module(mech('EtOHKonnov'), None)
     sch = stats['bk1_schedule']
