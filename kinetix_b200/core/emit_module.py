@@ -391,7 +391,7 @@ def emit_module(mech, fits, options=None, single_precision=False):
         tm_block = opt.get('bk1_tmem_block', 256)
         tm_ctas = opt.get('bk1_tmem_ctas', 1)            # CTAs per SM sharing the 512 columns
         tm_cols = 512 // tm_ctas
-        tm_slots = tm_cols // 2 // (tm_block // 128)     # doubles per thread: the columns are shared by block/128 warp groups
+        tm_slots = tm_cols // 2 // -(-tm_block // 128)    # doubles per thread: the columns are shared by block/128 warp groups
         cap = min(budget // (tm_block * tm_ctas * 8), opt.get('bk1_smem_cap', 1 << 30))
         need = bk1.smem_doubles_per_thread
         if (want_tm is True or need * 8 * 128 * 2 > budget) and need <= tm_slots + cap:
