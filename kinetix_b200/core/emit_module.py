@@ -322,13 +322,13 @@ def emit_module(mech, fits, options=None, single_precision=False):
     # stall samples sat on LDC: the second constant of an FFMA is an explicit load through the MIO queue), then
     # 3 CTAs x 168 registers instead of 4 x 128: 2800; NASA table through L1 2580, barriers 2760-2810, 2 CTAs 1930
 
-    def emit_bk1():
+    def emit_bk1(kernel_name='kx_bk1_f64'):
         if sp:
             e = BK1EmitterF32(mech, K)
             return e, e.emit('kx_bk1_f32', opt['block_bk1'], opt['minb_bk1'], opt.get('sync_every_f32', 0), opt['reorder'],
                              nasa_indexed=opt.get('nasa_indexed_f32', False))
         e = BK1Emitter(mech, K)
-        src = e.emit('kx_bk1_f64', opt['block_bk1'], opt['minb_bk1'], opt['sync_every'], opt['gibbs_in_smem'],
+        src = e.emit(kernel_name, opt['block_bk1'], opt['minb_bk1'], opt['sync_every'], opt['gibbs_in_smem'],
                      opt['reorder'], opt['prefetch'], opt['ring'], opt['pin_loads'], opt['l1_keep'], opt['keep_until'], opt['live_cap'], opt['eff_in_smem'], opt['nasa_indexed'],
                      tmem_slots=bk1_tm['slots'], smem_cap=bk1_tm['smem_cap'], tmem_cols=bk1_tm.get('cols', 512),
                      cold_uses=opt.get('cold_uses', 0), cold_slot_cap=opt.get('cold_slot_cap', 0),
@@ -421,6 +421,25 @@ def emit_module(mech, fits, options=None, single_precision=False):
     if changed:
         bk1, bk1_src = emit_bk1()
     bk1_smem = bk1.smem_doubles_per_thread * 8 * opt['block_bk1']
+    # small launches of the four-warp layout: below one wave the latency of ONE pass is all there is, and the classic
+    # layout's pass is shorter (GRI-3.0, 1 Ki - 16 Ki states: 51 vs 70 us; from 64 Ki states on the wide layout wins,
+    # 836 vs 579 M states/s).  The module carries the classic kernel as `kx_bk1_f64s` for launches of at most one wave of
+    # it.  Same schedule, hence the same NASA table (checked), one constant pool.
+    bk1_small = None
+    if wide and opt.get('bk1_small', True):
+        saved_opt, saved_tm = dict(opt), bk1_tm
+        opt.update(block_bk1=128, minb_bk1=4 if bk1.schedule_stats.get('peak_live', N) <= 21 else 3, sync_every=16,
+                   bk1_tmem=False, cold_uses=0, cold_conc_only=False, gibbs_prefer_tm=False)
+        bk1_tm = dict(slots=0, smem_cap=0)
+        e_s, src_s = emit_bk1('kx_bk1_f64s')
+        while e_s.smem_doubles_per_thread * 8 * 128 * opt['minb_bk1'] > budget and opt['minb_bk1'] > 1:
+            opt['minb_bk1'] -= 1
+            e_s, src_s = emit_bk1('kx_bk1_f64s')
+        if (e_s.nasa_lo_tab, e_s.nasa_hi_tab) == (bk1.nasa_lo_tab, bk1.nasa_hi_tab):
+            bk1_small = dict(src=src_s, block=128, minb=opt['minb_bk1'], smem=e_s.smem_doubles_per_thread * 8 * 128)
+        opt.clear()
+        opt.update(saved_opt)
+        bk1_tm = saved_tm
     out = []
     out.append('// GENERATED by kinetix_b200 -- mechanism-specialised sm_100a kernels. Do not edit.')
     out.append(f'// mechanism: {mech.name}  species: {N} (active {mech.n_active})  reactions: {mech.n_reactions}')
@@ -443,6 +462,8 @@ def emit_module(mech, fits, options=None, single_precision=False):
     if hasattr(bk1, 'nasa_table_definition'):
         out.append(bk1.nasa_table_definition())
     out.append(bk1_src)
+    if bk1_small:
+        out.append(bk1_small['src'])
 
     M = mech.molar_masses
     # constant bank budget (64 KB): pool + per-species tables; large mechanisms keep the tables that are
@@ -509,6 +530,22 @@ static int kxm_device() {{
   return dev >= 0 && dev < KXM_MAX_DEVICES ? dev : 0;
 }}
 ''')
+    small_cfg = small_launch = ''
+    if bk1_small:
+        pool_arg = ', kx_param_pool' if opt['param_constants'] else ''
+        small_cfg = (f"    if (int e = kxm_set_smem(kx_bk1_f64s<false>, {bk1_small['smem']})) return e;\n"
+                     f"    if (int e = kxm_set_smem(kx_bk1_f64s<true>, {bk1_small['smem']})) return e;\n")
+        small_launch = f'''  if (n <= (long long)n_sm[dev] * {bk1_small['block'] * bk1_small['minb']}) {{   // at most one wave of the classic layout
+    const unsigned g = (unsigned)((n + {bk1_small['block']} - 1) / {bk1_small['block']});
+    if (pfield)
+      kx_bk1_f64s<true><<<g, {bk1_small['block']}, {bk1_small['smem']}, stream>>>(n, offsetT, offset, pressure_R, pressure, log(pressure),
+                                                     (const double*)state, (double*)rates, Tref, (const double*)pfield{pool_arg});
+    else
+      kx_bk1_f64s<false><<<g, {bk1_small['block']}, {bk1_small['smem']}, stream>>>(n, offsetT, offset, pressure_R, pressure, log(pressure),
+                                                      (const double*)state, (double*)rates, Tref, nullptr{pool_arg});
+    return (int)cudaGetLastError();
+  }}
+'''
     if sp:
         out.append(f'''
 template <typename S>
@@ -533,13 +570,15 @@ static int launch_bk1(long long n, long long offsetT, long long offset, double p
   const int block = {opt['block_bk1']};
   const size_t smem = {bk1_smem};
   static bool configured[KXM_MAX_DEVICES] = {{}};
+  static int n_sm[KXM_MAX_DEVICES] = {{}};
   const int dev = kxm_device();
   if (!configured[dev]) {{
     if (int e = kxm_set_smem(kx_bk1_f64<false>, smem)) return e;
     if (int e = kxm_set_smem(kx_bk1_f64<true>, smem)) return e;
-    configured[dev] = true;
+    if (cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1002;
+{small_cfg}    configured[dev] = true;
   }}
-  const unsigned grid = (unsigned)((n + block - 1) / block);
+{small_launch}  const unsigned grid = (unsigned)((n + block - 1) / block);
   if (pfield)
     kx_bk1_f64<true><<<grid, block, smem, stream>>>(n, offsetT, offset, pressure_R, pressure, log(pressure),
                                                     (const double*)state, (double*)rates, Tref, (const double*)pfield{', kx_param_pool' if opt['param_constants'] else ''});

@@ -99,7 +99,9 @@ def bk1_source(mech_name, options=None, single_precision=False):
     """BK1 part of the module text (constants, NASA table, kernel) + launch shape, as emit_module plans it"""
     path = mech_name if os.path.exists(mech_name) else os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech_name + '.yaml')
     mech = load_mechanism(path)
-    src, stats = emit_module(mech, None, dict(options or {}), single_precision=single_precision)
+    opts = dict(options or {})
+    opts.setdefault('bk1_small', False)      # the small-launch instantiation IS the classic layout (emulated on request)
+    src, stats = emit_module(mech, None, opts, single_precision=single_precision)
     bk1 = src[:src.index('kx_rcpM[')]
     bk1 = bk1[:bk1.rindex('\n')]                    # drop the started table line
     m = re.search(r'__launch_bounds__\((\d+), (\d+)\)', bk1)

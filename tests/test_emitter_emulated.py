@@ -62,9 +62,10 @@ def test_generated_bk1_plog_and_pressure_field_on_cpu():
     {'bk1_tmem': True, 'live_cap': 10, 'bk1_smem_cap': 8},
     {'cold_uses': 15, 'cold_slot_cap': 90},                  # rarely used species: C_k / wdot_k in shared-memory slots
     {'cold_uses': 1000, 'cold_slot_cap': 120, 'live_cap': 14},
+    {'bk1_layout': 'classic'},       # three 128-thread CTAs, all slots in shared memory: the small-launch kernel's text
     {'cold_uses': 1000, 'cold_slot_cap': 90, 'cold_conc_only': True},    # C_k alone in a slot (heptaneLu88's layout)
     {'bk1_tmem': True, 'bk1_smem_cap': 30, 'cold_uses': 1000, 'cold_conc_only': True, 'gibbs_prefer_tm': True, 'live_cap': 16},
-], ids=['tm', 'tm_all', 'tm_2cta', 'live_cap', 'tm_live_cap', 'cold', 'cold_live_cap', 'cold_conc', 'tm_cold_conc'])
+], ids=['tm', 'tm_all', 'tm_2cta', 'live_cap', 'tm_live_cap', 'cold', 'cold_live_cap', 'classic', 'cold_conc', 'tm_cold_conc'])
 def test_generated_bk1_slot_layouts_on_cpu(options):
     emu = BK1Emulator('gri30', options)
     st = synthetic_states(53, 300, seed=7)

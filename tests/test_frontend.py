@@ -96,10 +96,14 @@ def test_bk1_scratch_slot_plan():
     sch = stats['bk1_schedule']
     assert '__launch_bounds__(256, 2)' in src and 'kx_tm_alloc_all<256>' in src and 'kx_tm_free_all<256>' in src
     assert 0 < sch['tmem_slots'] <= 64 and sch['smem_slots'] <= 53 and sch['cold_activations'] == 53
-    assert sch['smem_slots'] * 8 * 256 * 2 <= 220 * 1024 and '__syncthreads();\n  // ---- unit' not in src
+    assert sch['smem_slots'] * 8 * 256 * 2 <= 220 * 1024 and '__syncthreads();\n  // ---- unit' not in src[:src.index('kx_bk1_f64s(')]
+    # ... and the module carries the classic kernel for launches of at most one wave of it (same NASA table, one pool)
+    assert 'kx_bk1_f64s(' in src and 'kx_bk1_f64s<false><<<g, 128,' in src and src.count('kx_nasa_tab[') > 2
+    assert src.count('double kx_nasa_tab[') == 1 and '__launch_bounds__(128, 3)' in src
+    assert 'kx_bk1_f64s' not in emit_module(mech('gri30'), None, options={'bk1_small': False})[0]
     # the classic layout on request: three 128-thread CTAs at 168 registers, every slot in shared memory
     src, stats = emit_module(mech('gri30'), None, options={'bk1_layout': 'classic'})
-    assert 'kx_tm_alloc_all' not in src and '__launch_bounds__(128, 3)' in src
+    assert 'kx_tm_alloc_all' not in src and '__launch_bounds__(128, 3)' in src and 'kx_bk1_f64s' not in src
     assert stats['bk1_schedule']['tmem_slots'] == 0
     for name, bounds in (('LiDryer', '(128, 4)'), ('heptaneLu88', '(128, 3)'), ('NH3Konnov_edit', '(256, 2)'),
                          ('H2_Konnov', '(256, 2)')):

@@ -70,6 +70,32 @@ def test_bk1_matches_oracle_on_random_states(kinetix, mech):
     assert rate_err <= TOL and hrr_err <= TOL and e_sig <= TOL
 
 
+@pytest.mark.parametrize('mech', ['gri30', 'NH3Konnov_edit', 'H2_Konnov'])
+def test_bk1_small_and_wide_kernels_at_the_switch(kinetix, mech):
+    """Mechanisms with 10-36 live species carry two BK1 kernels: the four-warps-per-scheduler layout (two 256-thread CTAs
+    at 128 registers, concentrations in shared-memory slots, exp(+-g) in tensor memory) and the classic layout for
+    launches of at most one wave of it (SMs x CTAs per SM x 128 states).  Both sides of the switch against the oracle on
+    the same states, ragged sizes included; the two kernels agree with each other far inside the bound."""
+    import torch
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    p = P_ATM * (1.0 if mech != 'NH3Konnov_edit' else 3.7)       # inside the P-log tables
+    for ctas in (3, 4):                                           # the classic kernel runs 3 or 4 CTAs per SM
+        wave = n_sm * ctas * 128
+        st = synthetic_states(N, wave + 1, seed=77)
+        ref = orc.production_rates(st, p)
+        small = _run_bk1(kinetix, np.ascontiguousarray(st[:, :wave]), p / P_ATM)
+        wide = _run_bk1(kinetix, st, p / P_ATM)
+        for name, new, r in (('<= one wave', small, ref[:, :wave]), ('one wave + 1', wide, ref)):
+            rate_err, hrr_err = bk1_errors(new, r)
+            print(f'{mech} {new.shape[1]} states ({name}) BK1 vs {orc.kind}: rates {rate_err:.3e} hrr {hrr_err:.3e}')
+            assert np.isfinite(new).all() and rate_err <= TOL and hrr_err <= TOL
+        assert bk1_errors(small, wide[:, :wave])[0] <= 1e-12
+    tiny = synthetic_states(N, 77, seed=5)
+    assert bk1_errors(_run_bk1(kinetix, tiny, p / P_ATM), orc.production_rates(tiny, p))[0] <= TOL
+
+
 @pytest.mark.parametrize('mech', ['NH3Konnov_edit', 'chempolimi_edit'])
 def test_bk1_plog_mechanisms_across_pressures(kinetix, mech):
     """pressure-dependent-Arrhenius (P-log) reactions: below, inside and above the tabulated pressures
