@@ -54,6 +54,7 @@ def write_counts(module_dir):
         return best
     counts = dict(source_sha256=source_hash(module_dir),
                   bk1=pick('kx_bk1_f64ILb0') or pick('kx_bk1_f32IdLb0'),
+                  bk1_small=pick('kx_bk1_f64sILb0'),      # the classic layout carried for small launches: the minimal form
                   bk1_f32=pick('kx_bk1_f32IfLb0'),
                   bk2=pick('kx_bk2Id'), bk2_f32=pick('kx_bk2If'))
     with open(os.path.join(module_dir, 'counts.json'), 'w') as fh:
