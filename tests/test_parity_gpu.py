@@ -96,6 +96,61 @@ def test_bk1_small_and_wide_kernels_at_the_switch(kinetix, mech):
     assert bk1_errors(_run_bk1(kinetix, tiny, p / P_ATM), orc.production_rates(tiny, p))[0] <= TOL
 
 
+def test_wide_bk1_kernel_pitched_rows_and_pressure_field(kinetix):
+    """The four-warps-per-scheduler BK1 kernel (more than one wave of states) with what the small-size tests exercise on the
+    classic kernel only: species rows at a padded pitch behind a gap (offsetT / offset), T_ref != 1, p != p_ref, a ragged
+    last CTA -- nothing outside the addressed rows may be written -- and its per-state-pressure instantiation."""
+    mech = 'gri30'
+    kinetix.init(mech_path(mech))
+    N = kinetix.nSpecies()
+    p_ref, T_ref = 2.0e5, 1000.0
+    kinetix.build(p_ref, T_ref, [1.0 / N] * N, True)
+    orc = Oracle(mech)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    S = n_sm * 3 * 128 + 2 * 256 + 77             # beyond the small-launch switch, not a multiple of the CTA size
+    pitch = S + 13
+    st = synthetic_states(N, S, seed=4321, Tref=T_ref)
+    slab = np.full((N + 2) * pitch + 7, np.nan)
+    slab[0:S] = st[0]
+    offsetT = 7 + pitch
+    for k in range(N):
+        slab[offsetT + k * pitch: offsetT + k * pitch + S] = st[k + 1]
+    d_state = torch.from_numpy(slab).cuda()
+    d_rates = torch.full_like(d_state, float('nan'))
+    p = 3.0e5
+    kinetix.productionRates(S, offsetT, pitch, p / p_ref, d_state, d_rates)
+    torch.cuda.synchronize()
+    out = d_rates.cpu().numpy()
+    new = np.empty_like(st)
+    new[0] = out[0:S]
+    for k in range(N):
+        new[k + 1] = out[offsetT + k * pitch: offsetT + k * pitch + S]
+    ref = orc.production_rates(st, p, Tref=T_ref)
+    rate_err, hrr_err = bk1_errors(new, ref)
+    print(f'{mech} wide kernel, pitched rows: rates {rate_err:.3e} hrr {hrr_err:.3e}')
+    assert np.isfinite(new).all() and rate_err <= TOL and hrr_err <= TOL
+    mask = np.ones(out.shape, bool)
+    mask[0:S] = False
+    for k in range(N):
+        mask[offsetT + k * pitch: offsetT + k * pitch + S] = False
+    assert np.isnan(out[mask]).all(), 'the kernel wrote outside the addressed rows'
+    # one pressure per state through the same (wide) kernel: two groups against the scalar calls
+    field = np.where(np.arange(S) % 2 == 0, 0.5, 4.0)
+    d_p = torch.from_numpy(np.ascontiguousarray(field)).cuda()
+    d_rates.fill_(float('nan'))
+    kinetix.productionRatesPressureField(S, offsetT, pitch, d_p, d_state, d_rates)
+    torch.cuda.synchronize()
+    out = d_rates.cpu().numpy()
+    for g, pn in enumerate((0.5, 4.0)):
+        sel = np.arange(S) % 2 == g
+        got = np.empty((N + 1, int(sel.sum())))
+        got[0] = out[0:S][sel]
+        for k in range(N):
+            got[k + 1] = out[offsetT + k * pitch: offsetT + k * pitch + S][sel]
+        e = bk1_errors(got, orc.production_rates(np.ascontiguousarray(st[:, sel]), pn * p_ref, Tref=T_ref))
+        assert max(e) <= TOL, (pn, e)
+
+
 @pytest.mark.parametrize('mech', ['NH3Konnov_edit', 'chempolimi_edit'])
 def test_bk1_plog_mechanisms_across_pressures(kinetix, mech):
     """pressure-dependent-Arrhenius (P-log) reactions: below, inside and above the tabulated pressures
