@@ -312,8 +312,7 @@ class BK1Emitter:
     def emit(self, kernel_name='kx_bk1_f64', block=128, min_blocks=2, sync_every=8, gibbs_in_smem=True,
              reorder=True, prefetch=4, ring=0, pin_loads=False, l1_keep=False, keep_until=0, live_cap=0, eff_in_smem=True, nasa_indexed=False,
              tmem_slots=0, smem_cap=0, tmem_cols=512, cold_uses=0, cold_slot_cap=0, routine=False, kbase_ahead=0,
-             cold_conc_only=False, gibbs_prefer_tm=False, sync_scope='cta',
-             cold_volatile=False):
+             cold_conc_only=False, gibbs_prefer_tm=False):
         """block / min_blocks: launch bounds.
         routine: emit the reference-signature DEVICE FUNCTION `kinetix_species_rates(lnT, T, T2, T3, T4, rcpT, P, lnP,
           Ci, wdot)` (reference reaction_rates.py:560-562) instead of the kernel: concentrations come from `Ci[]`,
@@ -333,13 +332,11 @@ class BK1Emitter:
           shared memory while it lasts.  The kernel then allocates all 512 TMEM columns (one CTA per SM).
         sync_every: a CTA-wide barrier every that many reactions keeps the warps of a CTA inside the same
           window of the straight-line code so instruction-cache fills are shared (0 = none).
-          sync_scope='scheduler' (experiment, one 384-thread CTA): named barriers of the warps that share a scheduler
-          only, so that they find each other's lines in that scheduler's L0 instruction cache.  It does what it
-          says -- no_instruction 1.10 -> 0.57 stall cycles per issue, I-cache hit rate 60 -> 72 % -- and loses: warps
-          at the same place of the code wait for the same dependent chains at the same time (wait 1.78 -> 2.10,
-          long_scoreboard 0.79 -> 1.12): 854 / 883 / 905 / 933 M states/s for a barrier every 2 / 4 / 8 / 16 reactions
-          against 962 for three unsynchronised CTAs.  Sharing instruction fetches and covering each other's
-          latencies are opposite demands on the same three warps.
+          (Measured and removed: named barriers of the warps that share a SCHEDULER only, in one 384-thread CTA, so that
+          they find each other's lines in that scheduler's L0 instruction cache.  It does what it says -- no_instruction
+          1.10 -> 0.57 stall cycles per issue, I-cache hit rate 60 -> 72 % -- and loses: warps at the same place of the code
+          wait for the same dependent chains at the same time (wait 1.78 -> 2.10, long_scoreboard 0.79 -> 1.12): 854 / 883 /
+          905 / 933 M states/s for a barrier every 2 / 4 / 8 / 16 reactions against 962 for three unsynchronised CTAs.)
         gibbs_in_smem: exp(+-g_k) of live species in shared memory slots [slot][thread] (slots are recycled
           when a species retires) instead of registers.
         reorder: liveness-minimising reaction order (see _schedule).
@@ -590,9 +587,7 @@ class BK1Emitter:
         mem_cs, mem_wd, seg_of = {}, {}, {}
         self.cold_activations = 0
 
-        def CS(k, write=False):
-            if k in mem_cs and cold_volatile and not write:
-                return f'kx_lds_here(gs + {mem_cs[k]} * {block})'
+        def CS(k):
             return f'gs[{mem_cs[k]} * {block}]' if k in mem_cs else f'cs{k}'
 
         def WD(k):
@@ -676,9 +671,9 @@ class BK1Emitter:
             """species k becomes live: concentration, zeroed accumulator, exp(+-g_k/RT)"""
             place(k, seg_of.get(k, 0))
             if routine:
-                w(f'{CS(k, True)} = Ci[{k}]; {WD(k)} = 0.0;')
+                w(f'{CS(k)} = Ci[{k}]; {WD(k)} = 0.0;')
             elif k in self.kept and not reactivation:
-                w(f'{CS(k, True)} = w{k} * rho; {WD(k)} = 0.0;')
+                w(f'{CS(k)} = w{k} * rho; {WD(k)} = 0.0;')
             elif ring and not reactivation:
                 r = rank[k]
                 pending = max(0, min(ring - 1, len(act_order) - 1 - r))
@@ -690,15 +685,15 @@ class BK1Emitter:
             if routine or (k in self.kept and not reactivation):
                 pass
             elif reactivation:
-                w(f'{CS(k, True)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
+                w(f'{CS(k)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
             elif not ring and pin_loads:
                 # volatile max: keeps this activation ordered after the loads issued `prefetch` activations
                 # ahead (volatile asms are not reordered among themselves), so the compiler cannot sink those
                 # loads down to their first use
                 w(f'{{ double t; asm volatile("max.f64 %0, %1, 0d0000000000000000;" : "=d"(t) : "d"(y{k})); '
-                  f'{CS(k, True)} = t * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0; }}')
+                  f'{CS(k)} = t * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0; }}')
             else:
-                w(f'{CS(k, True)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
+                w(f'{CS(k)} = fmax(0.0, y{k}) * ({K(1. / m.species[k].M)} * rho); {WD(k)} = 0.0;')
             if not (need_pos[k] or need_neg[k]):
                 return
             c, _, _ = self.nasa_select(k, gcoef)
@@ -818,12 +813,7 @@ class BK1Emitter:
                 live_now += 1
             peak_live = max(peak_live, live_now)
             if sync_every and emitted and emitted // sync_every != (emitted + len(members)) // sync_every:
-                if sync_scope == 'scheduler':
-                    # only the warps that share a scheduler (warp index mod 4) wait for each other: they then find the
-                    # lines the first of them fetched in that scheduler's L0 instruction cache
-                    w(f'asm volatile("bar.sync %0, {block // 4};" ::"r"(((threadIdx.x >> 5) & 3) + 1) : "memory");')
-                else:
-                    w('__syncthreads();')
+                w('__syncthreads();')
             emitted += len(members)
             first_rx = m.reactions[members[0]]
             w(f'// ---- unit {pos}: reactions ' + ', '.join(str(i + 1) for i in members))

@@ -332,7 +332,7 @@ def emit_module(mech, fits, options=None, single_precision=False):
                      opt['reorder'], opt['prefetch'], opt['ring'], opt['pin_loads'], opt['l1_keep'], opt['keep_until'], opt['live_cap'], opt['eff_in_smem'], opt['nasa_indexed'],
                      tmem_slots=bk1_tm['slots'], smem_cap=bk1_tm['smem_cap'], tmem_cols=bk1_tm.get('cols', 512),
                      cold_uses=opt.get('cold_uses', 0), cold_slot_cap=opt.get('cold_slot_cap', 0),
-                     cold_conc_only=opt.get('cold_conc_only', False), gibbs_prefer_tm=opt.get('gibbs_prefer_tm', False), sync_scope=opt.get('sync_scope', 'cta'), cold_volatile=opt.get('cold_volatile', False),
+                     cold_conc_only=opt.get('cold_conc_only', False), gibbs_prefer_tm=opt.get('gibbs_prefer_tm', False),
                      kbase_ahead=opt.get('kbase_ahead', 0))
         return e, src
 

@@ -278,14 +278,6 @@ KX_DEVICE double kx_ld_keep(const double* p)
   asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
-// shared-memory load that stays where it is written (volatile: the compiler neither hoists it nor merges it with
-// another load of the same word)
-KX_DEVICE double kx_lds_here(const double* p)
-{
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-  return v;
-}
 KX_DEVICE void kx_st_stream(double* p, double v)
 {
   asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
