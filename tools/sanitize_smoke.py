@@ -19,7 +19,8 @@ for mech, sp in MECHS:
     kinetix.init(os.path.join(ROOT, 'kinetix_b200', 'mechanisms', mech + '.yaml'), single_precision=sp)
     N = kinetix.nSpecies()
     kinetix.build(101325.0, 1.0, [1.0 / N] * N, True)
-    S = 1555      # more than one persistent-CTA round of 512 states, ragged tail
+    # more than one persistent-CTA round of 512 states, ragged tail; KX_SMOKE_STATES=60001 reaches the wide BK1 kernel
+    S = int(os.environ.get('KX_SMOKE_STATES', '1555'))
     st = torch.from_numpy(synthetic_states(N, S)).cuda()
     r = torch.empty_like(st)
     v = torch.empty(S, dtype=torch.float64, device='cuda')
