@@ -185,6 +185,7 @@ KX_DEVICE void kx_sts_if(unsigned addr, double v, bool p)
 {
   asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}" ::"r"(addr), "d"(v), "r"((unsigned)p) : "memory");
 }
+template <int V> struct kx_int { static constexpr int value = V; };    // compile-time tag for generic lambdas
 KX_DEVICE void kx_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 KX_DEVICE void kx_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -265,6 +266,8 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
     if constexpr (L > 1) {
       kx_tm_wait_st();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      // (a named barrier of the two partner warps only -- everything the halves exchange belongs to their own states --
+      // measured 119.5 vs 118.9 M states/s on EtOHKonnov: not worth a second kind of barrier in the kernel)
       __syncthreads();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
@@ -665,8 +668,9 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll
         for (int p = 0; p < P; p++) kx_tm_load<G>(KX_TM(p, jb * TB + half * G), cur[p]);
         const real* __restrict__ tile = acquire();
+        // (L = 2: exactly one group per half -- a trip count the compiler can see, no loop test)
 #pragma unroll 1
-        for (int j0 = half * G; j0 < TB; j0 += L * G) {
+        for (int j0 = half * G, once = 0; L == 1 ? j0 < TB : once < 1; j0 += L * G, once++) {
           real sj[P][G];
           kx_tm_wait_ld();
 #pragma unroll
@@ -729,27 +733,33 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
         if constexpr (L == 1) kx_tm_wait_ld();       // the look-ahead load of the last group
         release();
       }
-      // diagonal tile: pairs i > j inside the block
+      // diagonal tile: pairs i > j inside the block.  The halves (L = 2) take alternate pairs; WHICH half this warp is
+      // is decided once, outside the unrolled pair list (a test per pair is a branch per ten instructions: the phase
+      // ran at 21 % pipe utilisation and took 10 % of EtOHKonnov's time for 4 % of its work)
       {
         const real* __restrict__ tile = acquire();
+        auto diagonal = [&](auto which) {
+          constexpr int H = decltype(which)::value;
 #pragma unroll
-        for (int i = 1; i < TB; i++) {
+          for (int i = 1; i < TB; i++) {
 #pragma unroll
-          for (int j = 0; j < i; j++) {
-            if (L > 1 && ((i + j) & (L - 1)) != half) continue;      // the halves take alternate pairs
-            // coefficient m of pair (i, j): paired rows interleaved, the odd last row on its own (see KX_COL)
-            const real* cp = tile + j * KX_COL + (i / 2) * 10 + ((i | 1) < TB ? (i & 1) : 0);
-            const int cs = (i | 1) < TB ? 2 : 1;
-            const real c0 = cp[0], c1 = cp[cs], c2 = cp[2 * cs], c3 = cp[3 * cs], c4 = cp[4 * cs];
+            for (int j = 0; j < i; j++) {
+              if (L > 1 && ((i + j) & (L - 1)) != H) continue;
+              // coefficient m of pair (i, j): paired rows interleaved, the odd last row on its own (see KX_COL)
+              const real* cp = tile + j * KX_COL + (i / 2) * 10 + ((i | 1) < TB ? (i & 1) : 0);
+              const int cs = (i | 1) < TB ? 2 : 1;
+              const real c0 = cp[0], c1 = cp[cs], c2 = cp[2 * cs], c3 = cp[3 * cs], c4 = cp[4 * cs];
 #pragma unroll
-            for (int p = 0; p < P; p++) {
-              const real q = fma(c4, lnT4[p], fma(fma(c3, lnT[p], c2), lnT2[p], fma(c1, lnT[p], c0)));
-              const real d = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
-              sk[p][i] = fma(xk[p][j], d, sk[p][i]);
-              sk[p][j] = fma(xk[p][i], d, sk[p][j]);
+              for (int p = 0; p < P; p++) {
+                const real q = fma(c4, lnT4[p], fma(fma(c3, lnT[p], c2), lnT2[p], fma(c1, lnT[p], c0)));
+                const real d = KX_RCP_DIFF ? q : KX_PAIR_RCP(q);
+                sk[p][i] = fma(xk[p][j], d, sk[p][i]);
+                sk[p][j] = fma(xk[p][i], d, sk[p][j]);
+              }
             }
           }
-        }
+        };
+        if (L == 1 || half == 0) diagonal(kx_int<0>{}); else diagonal(kx_int<1>{});
         release();
       }
       // S_k of this block are final (L = 2: after the halves have added their partial sums):
@@ -763,24 +773,28 @@ kx_bk2(const long long n_states, const long long offsetT, const long long offset
 #pragma unroll
       for (int p = 0; p < P; p++) kx_tm_load<2>(KX_TM(p, KX_NS), praw[p]);
       kx_tm_wait_ld();
+      auto store_rows = [&](auto which) {          // each half stores the rows of its half of the block
+        constexpr int H = decltype(which)::value;
 #pragma unroll
-      for (int p = 0; p < P; p++) {
-        real park[2];
-        kx_tm_unpack<2>(praw[p], park);
-        const real Mb = park[0], f = park[1] * (real)(1.0 / 8.31446261815324);   // rho*T^1.5/(p*Mbar) = sqrt(T)/R
-        const bool lv = is_live(p);
-        ST* const dst = rhoD + state_id(batch, p) + (size_t)(kb * TB) * offset;
+        for (int p = 0; p < P; p++) {
+          real park[2];
+          kx_tm_unpack<2>(praw[p], park);
+          const real Mb = park[0], f = park[1] * (real)(1.0 / 8.31446261815324);   // rho*T^1.5/(p*Mbar) = sqrt(T)/R
+          const bool lv = is_live(p);
+          ST* const dst = rhoD + state_id(batch, p) + (size_t)(kb * TB) * offset;
 #pragma unroll
-        for (int i = 0; i < TB; i++) {
-          if (L > 1 && (i / (TB / L)) != half) continue;       // each half stores the rows of its half of the block
-          const int k = kb * TB + i;
-          if (k < KX_N) {
-            const real num = fma(-kx_M[k], xk[p][i], Mb);
-            const real v = f * num * kx_rcp(sk[p][i]);
-            if (lv) kx_st_stream(dst + (size_t)i * offset, (ST)v);
+          for (int i = 0; i < TB; i++) {
+            if (L > 1 && (i / (TB / L)) != H) continue;
+            const int k = kb * TB + i;
+            if (k < KX_N) {
+              const real num = fma(-kx_M[k], xk[p][i], Mb);
+              const real v = f * num * kx_rcp(sk[p][i]);
+              if (lv) kx_st_stream(dst + (size_t)i * offset, (ST)v);
+            }
           }
         }
-      }
+      };
+      if (L == 1 || half == 0) store_rows(kx_int<0>{}); else store_rows(kx_int<1>{});
       meet();       // both halves are done with the block's X rows and with the exchange areas
       // the block's X rows are dead: the next batch's mass fractions move in
 #ifndef KX_BK2_NO_PREFETCH
