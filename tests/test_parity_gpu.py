@@ -225,6 +225,41 @@ def test_bk2_matches_oracle_on_random_states(kinetix, mech):
     assert max(errs) <= TOL
 
 
+def test_bk2_last_round_goes_to_a_second_launch(kinetix):
+    """Persistent BK2 CTAs take batches round-robin; when the last round would occupy at most half the SMs, its states
+    are handled by a second launch of the one-state-per-thread instantiation (pointer-shifted buffers).  Every element
+    on both sides of that split, ragged end included, against the oracle; a pitched layout as well."""
+    mech = 'gri30'
+    N = _setup(kinetix, mech)
+    orc = Oracle(mech)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    S = n_sm * 512 * 2 + 10 * 512 + 77                      # two full rounds + 11 batches (the last one ragged)
+    st = synthetic_states(N, S, seed=2025)
+    cond, visc, rhoD = _run_bk2(kinetix, st, 1.0)
+    rc, rv, rrd = orc.transport(st, 1.0)
+    split = n_sm * 512 * 2
+    for name, sl in (('main launch', slice(0, split)), ('tail launch', slice(split, S))):
+        errs = rel_err(cond[sl], rc[sl]), rel_err(visc[sl], rv[sl]), rel_err(rhoD[:, sl], rrd[:, sl])
+        print(f'{mech} BK2 {name}: {errs}')
+        assert np.isfinite(rhoD[:, sl]).all() and max(errs) <= TOL
+    # pitched rows behind a gap: the shifted pointers of the tail launch must respect offsetT / offset
+    pitch = S + 11
+    slab = np.full((N + 2) * pitch + 5, np.nan)
+    slab[0:S] = st[0]
+    offsetT = 5 + pitch
+    for k in range(N):
+        slab[offsetT + k * pitch: offsetT + k * pitch + S] = st[k + 1]
+    d_state = torch.from_numpy(slab).cuda()
+    d_visc = torch.full((S,), float('nan'), dtype=torch.float64, device='cuda')
+    d_cond = torch.full_like(d_visc, float('nan'))
+    d_rhoD = torch.full((N * pitch,), float('nan'), dtype=torch.float64, device='cuda')
+    kinetix.mixtureAvgTransportProps(S, offsetT, pitch, 1.0, d_state, d_visc, d_cond, d_rhoD)
+    torch.cuda.synchronize()
+    out = d_rhoD.cpu().numpy().reshape(N, pitch)
+    assert np.array_equal(out[:, :S], rhoD) and np.isnan(out[:, S:]).all()
+    assert np.array_equal(d_visc.cpu().numpy(), visc) and np.array_equal(d_cond.cpu().numpy(), cond)
+
+
 def test_gri30_one_million_states_full_compare(kinetix):
     """BASELINE configs 1 and 2 at their stated size: 1 Mi seeded GRI-3.0 states, EVERY output element of BK1 and
     BK2 compared with the reference's own generated code (oracle/_ref on all host cores, ~20 s).  1 Mi states =

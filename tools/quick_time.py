@@ -28,7 +28,7 @@ N = kinetix.nSpecies()
 kinetix.build(101325.0, 1.0, [1.0 / N] * N, True)
 S = a.n
 base = torch.from_numpy(synthetic_states(N, 1 << 16, seed=1)).cuda()
-st = base.repeat(1, S // (1 << 16)).contiguous().to(tdt)
+st = base.repeat(1, -(-S // (1 << 16)))[:, :S].contiguous().to(tdt)      # (any S, not only multiples of 64 Ki)
 rates = torch.empty_like(st)
 visc = torch.empty(S, dtype=tdt, device='cuda')
 cond = torch.empty_like(visc)
